@@ -1,0 +1,66 @@
+"""ctypes loader of ``libdtfft_b200.so`` (the C ABI declared in ``include/dtfft_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C dtfft_b200/csrc``.
+There is NO CPU fallback: if the shared object is missing every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdtfft_b200.so")
+
+_lib = None
+
+
+class DtfftB200Error(RuntimeError):
+    """Non-zero return code of the C ABI (dtfft_error_t or DTFFTB_ERROR_*)."""
+
+    def __init__(self, code: int, where: str):
+        self.code = int(code)
+        super().__init__(f"{where} failed with code {self.code} ({describe_error(self.code)})")
+
+
+def describe_error(code: int) -> str:
+    if code <= -30000:
+        return "internal invariant violated"
+    if code <= -20000:
+        return f"NCCL error {-(code + 20000)}"
+    if code <= -10000:
+        return f"CUDA error {-(code + 10000)}"
+    return "dtfft_error_t"
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C dtfft_b200/csrc`. dtfft_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.dtfftb_version.restype = C.c_char_p
+    L.dtfftb_device_available.restype = C.c_int
+    L.dtfftb_kernel_create.argtypes = [C.POINTER(vp), C.c_int, i32p, C.c_int, C.c_int64, i32p, C.c_int, C.c_int, C.c_int]
+    L.dtfftb_kernel_execute.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int]
+    L.dtfftb_kernel_execute_all.argtypes = [vp, vp, vp, vp]
+    L.dtfftb_kernel_set_peer_out.argtypes = [vp, C.POINTER(vp), i64p]
+    L.dtfftb_kernel_destroy.argtypes = [C.POINTER(vp)]
+    L.dtfftb_kernel_get_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 5 + [i64p]
+    L.dtfftb_kernel_set_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.dtfftb_kernel_autotune.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    for name in ("dtfftb_kernel_create", "dtfftb_kernel_execute", "dtfftb_kernel_execute_all",
+                 "dtfftb_kernel_set_peer_out", "dtfftb_kernel_destroy", "dtfftb_kernel_get_info",
+                 "dtfftb_kernel_set_tile", "dtfftb_kernel_autotune"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(code: int, where: str) -> None:
+    if code != 0:
+        raise DtfftB200Error(code, where)

@@ -1,0 +1,113 @@
+/*
+ * dtfft_b200.h -- C ABI of the B200-native dtFFT reshape path (libdtfft_b200.so).
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only.  Each group of entry
+ * points replaces one Fortran class of the reference (ShatrovOA/dtFFT v3.2.0); the
+ * reference interface it stands in for is cited as file:line.  The Fortran host code of
+ * the reference reaches these through iso_c_binding (see INTEGRATION.md for the stubs).
+ *
+ * All functions return 0 (DTFFT_SUCCESS) or a dtfft_error_t value from
+ * include/dtfft_config.h.in:82-151 of the reference; CUDA / NCCL failures, which the
+ * reference turns into MPI_Abort (src/include/_dtfft_cuda.h:7-21), are returned as
+ * DTFFTB_ERROR_CUDA_BASE - cudaError_t (resp. DTFFTB_ERROR_NCCL_BASE - ncclResult_t) so
+ * that the caller decides.  Not thread-safe (like the reference): one call at a time.
+ */
+#ifndef DTFFT_B200_H
+#define DTFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTFFTB_ERROR_CUDA_BASE (-10000)
+#define DTFFTB_ERROR_NCCL_BASE (-20000)
+#define DTFFTB_ERROR_INTERNAL (-30000) /* invariant violated (reference: INTERNAL_ERROR) */
+
+/* kernel_type_t values: src/dtfft_abstract_kernel.F90:59-98 */
+enum {
+    DTFFTB_KERNEL_DUMMY = -1,
+    DTFFTB_KERNEL_PACK = 1,
+    DTFFTB_KERNEL_COPY_PIPELINED = 2,
+    DTFFTB_KERNEL_UNPACK = 3,
+    DTFFTB_KERNEL_COPY = 4,
+    DTFFTB_KERNEL_UNPACK_PIPELINED = 5,
+    DTFFTB_KERNEL_PACK_PIPELINED = 6,
+    DTFFTB_KERNEL_PERMUTE_FORWARD = 7,
+    DTFFTB_KERNEL_PERMUTE_BACKWARD = 8,
+    DTFFTB_KERNEL_PERMUTE_BACKWARD_START = 9,
+    DTFFTB_KERNEL_PERMUTE_BACKWARD_END = 10,
+    DTFFTB_KERNEL_PERMUTE_BACKWARD_END_PIPELINED = 11,
+    DTFFTB_KERNEL_PACK_FORWARD = 12,
+    DTFFTB_KERNEL_PACK_BACKWARD = 13,
+    /* host-only in the reference (src/dtfft_kernel_device.F90:72-74); available on device here */
+    DTFFTB_KERNEL_UNPACK_FORWARD = 15,
+    DTFFTB_KERNEL_UNPACK_FORWARD_PIPELINED = 16,
+    DTFFTB_KERNEL_UNPACK_BACKWARD = 17,
+    DTFFTB_KERNEL_UNPACK_BACKWARD_PIPELINED = 18
+};
+
+/* ------------------------------------------------------------------------------------
+ * Kernel plugin surface -- replaces kernel_device / nvrtc_module / nvrtc_block_optimizer
+ * / nvrtc_module_cache (src/dtfft_kernel_device.F90:45-178, src/dtfft_nvrtc_module.F90,
+ * src/dtfft_nvrtc_block_optimizer.F90, src/dtfft_nvrtc_module_cache.F90) behind the
+ * deferred interface of abstract_kernel (src/dtfft_abstract_kernel.F90:137-163).
+ * ---------------------------------------------------------------------------------- */
+typedef struct dtfftb_kernel_s* dtfftb_kernel_t;
+
+/* abstract_kernel%create (src/dtfft_abstract_kernel.F90:219-288) + kernel_device%create
+ * (src/dtfft_kernel_device.F90:61-102).
+ *   dims[ndims]        local extents, dims[0] fastest (ndims = 2 or 3)
+ *   kernel_type        DTFFTB_KERNEL_*
+ *   base_storage       bytes per element: 4, 8 or 16
+ *   neighbor_data      5 x n_neighbors int32, column-major exactly like the Fortran
+ *                      neighbor_data(5, P): (n1, n2, n3, in displ, out displ) per peer, in
+ *                      elements; NULL for the whole-buffer permutes / KERNEL_COPY
+ *   effort             dtfft_effort_t value (0..3); force_effort as in the reference
+ * Zero-volume dims or KERNEL_DUMMY give a valid handle whose execute is a no-op. */
+int dtfftb_kernel_create(dtfftb_kernel_t* kernel, int ndims, const int32_t* dims, int kernel_type,
+                         int64_t base_storage, const int32_t* neighbor_data, int n_neighbors, int effort,
+                         int force_effort);
+
+/* abstract_kernel%execute (src/dtfft_abstract_kernel.F90:290-403) + kernel_device%execute
+ * (src/dtfft_kernel_device.F90:104-178).  `stream` is a cudaStream_t.  `neighbor` is
+ * 1-based and required (> 0) for the per-peer kinds (*_PIPELINED, PACK_FORWARD,
+ * PACK_BACKWARD); pass 0 otherwise.  All peers of the non-pipelined kinds are covered by
+ * ONE launch.  `sync` != 0 synchronises the stream after the launch. */
+int dtfftb_kernel_execute(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int neighbor, int sync);
+
+/* Extension used by the fused P2P backend: run the per-peer kind for EVERY peer in one
+ * launch (what the reference does with P launches of pack_forward/pack_backward in its
+ * fused backends, src/dtfft_backend_mpi.F90:474-624). */
+int dtfftb_kernel_execute_all(dtfftb_kernel_t kernel, const void* in, void* out, void* stream);
+
+/* Extension: per-peer destination bases (peer-mapped device pointers).  When set, block n
+ * is written at out_bases[n] + out displacement instead of `out` (pack fused into the
+ * remote NVLink store).  Pass NULL to clear.  `out_displs_override` (elements, may be
+ * NULL) replaces neighbor_data(5, n) -- the receive displacement on the peer. */
+int dtfftb_kernel_set_peer_out(dtfftb_kernel_t kernel, void* const* out_bases, const int64_t* out_displs_override);
+
+/* abstract_kernel%destroy.  Sets *kernel to NULL. */
+int dtfftb_kernel_destroy(dtfftb_kernel_t* kernel);
+
+/* Introspection (used by tests, autotune and `report`). */
+int dtfftb_kernel_get_info(dtfftb_kernel_t kernel, int* family /*0 none,1 copy,2 transpose,3 rows*/,
+                           int* unit_bytes, int* tile_a, int* tile_b, int* threads, int64_t* n_items);
+/* Override the family-T tile (ka, kb in multiples of 32 elements; rows = threadIdx.y extent). */
+int dtfftb_kernel_set_tile(dtfftb_kernel_t kernel, int ka, int kb, int rows);
+/* Time every supported tile configuration on (in, out) and keep the fastest -- the
+ * reference's timed kernel autotune (src/dtfft_kernel_device.F90:338-397). Returns best ms. */
+int dtfftb_kernel_autotune(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
+                           int n_iters, float* best_ms);
+
+/* Library info */
+const char* dtfftb_version(void);
+/* 1 if a CUDA device is usable in this process, else 0 (never falls back to CPU). */
+int dtfftb_device_available(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTFFT_B200_H */
