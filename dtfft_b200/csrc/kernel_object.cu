@@ -290,12 +290,9 @@ int Kernel::create(int ndims, const int32_t* dims, int kernel_type, int64_t base
 
     // B200 tile table (replaces nvrtc_block_optimizer's Volta/Ampere model).
     if (family_ == FAM_T) {
-        if (es_ == 16)
-            tile_ = TileCfg{1, 1, 8};
-        else if (es_ == 8)
-            tile_ = TileCfg{2, 2, 16};
-        else
-            tile_ = TileCfg{2, 2, 8};
+        // measured on B200 at 512^3 (profiles/r01_kbench.md): 64x64 tiles, 256 threads win for
+        // 4-, 8- and 16-byte elements (6.2-6.4 TB/s vs 6.5 TB/s for a plain device copy)
+        tile_ = TileCfg{2, 2, 8};
         if (const char* e = getenv("DTFFTB_TILE")) {
             int ka, kb, r;
             if (sscanf(e, "%d,%d,%d", &ka, &kb, &r) == 3 && transpose_cfg_supported((int)es_, TileCfg{ka, kb, r}))
@@ -332,7 +329,7 @@ int Kernel::rebuild_tables() {
     if (d_blocks_) cudaFree(d_blocks_);
     d_blocks_ = nullptr;
     std::vector<BlockDesc> host;
-    int grid_mult = 1;
+    int grid_mult = 4;  // CTAs per resident slot: >1 lets the hardware scheduler even out the tail
     if (const char* e = getenv("DTFFTB_GRID_MULT")) grid_mult = std::max(1, atoi(e));
 
     auto make_desc = [&](const Box& b, int t0, int t1, long long begin, int peer) {

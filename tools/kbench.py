@@ -9,10 +9,11 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_kernels as R  # noqa: E402  (A/B baseline only)
 from dtfft_b200.kernel import (KERNEL_PERMUTE_BACKWARD, KERNEL_PERMUTE_BACKWARD_START, KERNEL_PERMUTE_FORWARD,  # noqa: E402
                                KERNEL_UNPACK, KERNEL_PERMUTE_BACKWARD_END, Kernel)
 
-TILES = [(1, 1, 4), (1, 1, 8), (1, 1, 16), (2, 1, 8), (1, 2, 8), (2, 2, 8), (2, 2, 16)]
+TILES = [(1, 1, 8), (2, 1, 8), (1, 2, 8), (2, 2, 8), (2, 2, 16)]
 
 
 def time_ms(fn, warmup=3, iters=10):
@@ -55,12 +56,23 @@ def main():
                          (KERNEL_PERMUTE_BACKWARD_START, "backward_start")):
             k = Kernel().create([n, n, n], 0, es, kt)
             for tile in TILES:
-                for gm in (1, 4):
+                for gm in (4, 16, 64):
                     os.environ["DTFFTB_GRID_MULT"] = str(gm)
                     k.set_tile(*tile)
                     ms = time_ms(lambda: k.execute(a, b))
                     emit({"what": name, "es": es, "n": n, "tile": tile, "grid_mult": gm, "ms": ms, "gbs": gb / ms * 1e3})
             k.destroy()
+            # the kernel to beat: the reference's generated kernel, best of its candidate configs
+            if R.available():
+                best = None
+                for (t, r) in R.configs():
+                    if not R.valid_config(es, t, r):
+                        continue
+                    ms = time_ms(lambda: R.launch(kt, [n, n, n], es, t, r, b.data_ptr(), a.data_ptr()), iters=5)
+                    rec = {"what": "REF_" + name, "es": es, "n": n, "tile": [t, r], "ms": ms, "gbs": gb / ms * 1e3}
+                    emit(rec)
+                    best = rec if best is None or ms < best["ms"] else best
+                emit(dict(best, what="REF_BEST_" + name))
         # multi-peer unpack / backward_end as produced by an 8-rank slab transposition
         P = 8
         for kt, name in ((KERNEL_UNPACK, "unpack8"), (KERNEL_PERMUTE_BACKWARD_END, "backward_end8")):
@@ -70,7 +82,17 @@ def main():
                 nd[i] = (nxx, n, n, i * nxx * n * n, i * nxx)
             if name == "backward_end8":
                 pass
-            for gm in (1, 4):
+            if R.available():
+                per = {KERNEL_UNPACK: 5, KERNEL_PERMUTE_BACKWARD_END: 11}[kt]
+                for (t, r) in ((32, 8), (32, 4), (64, 8), (16, 16)):
+                    if not R.valid_config(es, t, r):
+                        continue
+                    def ref_all():
+                        for i in range(P):
+                            R.launch(per, [n, n, n], es, t, r, b.data_ptr(), a.data_ptr(), nd[i])
+                    ms = time_ms(ref_all, iters=5)
+                    emit({"what": "REF_" + name, "es": es, "n": n, "tile": [t, r], "ms": ms, "gbs": gb / ms * 1e3})
+            for gm in (1, 4, 16):
                 os.environ["DTFFTB_GRID_MULT"] = str(gm)
                 k = Kernel().create([n, n, n], 0, es, kt, nd)
                 ms = time_ms(lambda: k.execute(a, b))
