@@ -46,10 +46,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, ~2 ms period)."""
 
     def __init__(self, index=0):
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -58,23 +55,38 @@ class ClockSampler:
         self.index = index
 
     def _run(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self._stop.wait(0.002)
+        except Exception as ex:  # NVML missing: fall back to one nvidia-smi query
+            self.error = str(ex)
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
                 f = [x.strip() for x in out.split(",")]
                 self.samples.append(float(f[0]))
                 self.max_mhz = float(f[1])
-                for nm, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):

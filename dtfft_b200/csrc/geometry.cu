@@ -1,0 +1,272 @@
+// Decomposition and per-peer block geometry (see geometry.h for the reference citations).
+// Pure host code; compiled by nvcc only to keep one toolchain for the library.
+#include "geometry.h"
+
+#include <cmath>
+#include <cstdlib>
+
+#include "kernel_object.h"
+
+namespace dtfftb {
+
+void local_size(int n_global, int comm_dim, int comm_rank, int32_t* start, int32_t* count) {
+    // remainder goes to the LAST (n mod p) ranks: src/dtfft_pencil.F90:255-267
+    if (comm_dim == 1) {
+        *start = 0;
+        *count = n_global;
+        return;
+    }
+    const int res = n_global % comm_dim, base = n_global / comm_dim;
+    int s = 0;
+    for (int q = 0; q < comm_rank; ++q) s += base + (q >= comm_dim - res ? 1 : 0);
+    *start = s;
+    *count = base + (comm_rank >= comm_dim - res ? 1 : 0);
+}
+
+void dims_create(int nnodes, int ndims, int32_t* dims) {
+    int fixed = 1, nfree = 0, f0 = -1, f1 = -1;
+    for (int i = 0; i < ndims; ++i) {
+        if (dims[i] > 0)
+            fixed *= dims[i];
+        else {
+            if (nfree == 0) f0 = i;
+            if (nfree == 1) f1 = i;
+            ++nfree;
+        }
+    }
+    const int rem = nnodes / fixed;
+    if (nfree == 1) {
+        dims[f0] = rem;
+    } else if (nfree == 2) {
+        // balanced factorisation, larger factor first (what MPI_Dims_create returns for two free dims)
+        int b = (int)std::floor(std::sqrt((double)rem));
+        while (b > 1 && rem % b) --b;
+        if (b < 1) b = 1;
+        dims[f0] = rem / b;
+        dims[f1] = b;
+    }
+}
+
+GridChoice choose_grid(int ndims, const int32_t* dims, int comm_size, bool cuda, bool z_slab_enabled,
+                       bool y_slab_enabled) {
+    // src/dtfft_transpose_plan.F90:170-203 (non-cartesian communicator)
+    GridChoice g;
+    int32_t cd[3] = {1, 0, 0};
+    bool cond1 = comm_size <= dims[ndims - 1];
+    bool cond2 = comm_size <= dims[0] && comm_size <= dims[1];
+    if (cuda) {
+        cond1 = kDefTileSize <= dims[ndims - 1] / comm_size;
+        cond2 = kDefTileSize <= dims[0] / comm_size && kDefTileSize <= dims[1] / comm_size;
+    }
+    if (ndims == 3) {
+        if (cond1 && z_slab_enabled) {
+            cd[1] = 1, cd[2] = comm_size, g.is_z_slab = true;
+        } else if (cond2 && y_slab_enabled) {
+            cd[1] = comm_size, cd[2] = 1, g.is_y_slab = true;
+        } else if (cond1) {
+            cd[1] = 1, cd[2] = comm_size;
+        } else if (cond2) {
+            cd[1] = comm_size, cd[2] = 1;
+        }
+    }
+    dims_create(comm_size, ndims, cd);
+    for (int i = 0; i < ndims; ++i) g.comm_dims[i] = cd[i];
+    if (dims[ndims - 2] < cd[ndims - 2] || dims[ndims - 1] < cd[ndims - 1]) g.invalid_grid = true;
+    return g;
+}
+
+void cart_coords(int rank, int ndims, const int32_t* comm_dims, int32_t* coords) {
+    for (int d = ndims - 1; d >= 0; --d) {
+        coords[d] = rank % comm_dims[d];
+        rank /= comm_dims[d];
+    }
+}
+
+int cart_rank(int ndims, const int32_t* comm_dims, const int32_t* coords) {
+    int r = 0;
+    for (int d = 0; d < ndims; ++d) r = r * comm_dims[d] + coords[d];
+    return r;
+}
+
+std::vector<int> comm_members(int rank, int ndims, const int32_t* comm_dims, int comm_id) {
+    std::vector<int> out;
+    int n = 1;
+    for (int d = 0; d < ndims; ++d) n *= comm_dims[d];
+    if (comm_id == 1) {  // helper%comms(1) = base (cartesian) communicator, abstract_backend.F90:408
+        for (int r = 0; r < n; ++r) out.push_back(r);
+        return out;
+    }
+    int32_t coords[3];
+    cart_coords(rank, ndims, comm_dims, coords);
+    for (int c = 0; c < comm_dims[comm_id - 1]; ++c) {
+        int32_t cc[3] = {coords[0], coords[1], coords[2]};
+        cc[comm_id - 1] = c;
+        out.push_back(cart_rank(ndims, comm_dims, cc));
+    }
+    return out;
+}
+
+void permutations(int ndims, int dperm[3][3], int cperm[3][3]) {
+    // src/dtfft_transpose_plan.F90:1046-1082, 0-based
+    if (ndims == 2) {
+        const int dp[2][2] = {{0, 1}, {1, 0}}, cp[2][2] = {{0, 1}, {0, 1}};
+        for (int d = 0; d < 2; ++d)
+            for (int j = 0; j < 2; ++j) dperm[d][j] = dp[d][j], cperm[d][j] = cp[d][j];
+        return;
+    }
+    const int dp[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}}, cp[3][3] = {{0, 1, 2}, {0, 2, 1}, {0, 1, 2}};
+    for (int d = 0; d < 3; ++d)
+        for (int j = 0; j < 3; ++j) dperm[d][j] = dp[d][j], cperm[d][j] = cp[d][j];
+}
+
+void make_pencils(int ndims, const int32_t* dims, const int32_t* comm_dims, int rank, Pencil out[3]) {
+    int dperm[3][3], cperm[3][3];
+    permutations(ndims, dperm, cperm);
+    int32_t coords[3];
+    cart_coords(rank, ndims, comm_dims, coords);
+    for (int d = 0; d < ndims; ++d) {
+        Pencil& p = out[d];
+        p = Pencil{};
+        p.aligned_dim = d + 1;
+        p.ndims = ndims;
+        p.is_even = true;
+        for (int j = 0; j < ndims; ++j) {
+            const int g = cperm[d][j];
+            local_size(dims[dperm[d][j]], comm_dims[g], coords[g], &p.starts[j], &p.counts[j]);
+            if (comm_dims[g] > 1 && dims[dperm[d][j]] % comm_dims[g] != 0) p.is_even = false;
+        }
+        p.is_distributed = false;  // fastest axis is never split in the default decomposition
+    }
+}
+
+int transpose_comm_id(int ttype) {
+    switch (std::abs(ttype)) {
+        case 1: return 2;
+        case 2: return 3;
+        default: return 1;
+    }
+}
+
+void transpose_pencil_ids(int ttype, int* send, int* recv) {
+    switch (ttype) {
+        case T_X_TO_Y: *send = 0, *recv = 1; break;
+        case T_Y_TO_X: *send = 1, *recv = 0; break;
+        case T_Y_TO_Z: *send = 1, *recv = 2; break;
+        case T_Z_TO_Y: *send = 2, *recv = 1; break;
+        case T_X_TO_Z: *send = 0, *recv = 2; break;
+        default: *send = 2, *recv = 0; break;  // Z_TO_X
+    }
+}
+
+HandleGeometry transpose_geometry(int ttype, const std::vector<Pencil>& send_by_member,
+                                  const std::vector<Pencil>& recv_by_member, int me, const std::vector<int>& members,
+                                  bool pipelined, bool fused) {
+    const int p = (int)members.size();
+    const Pencil& send = send_by_member[me];
+    const Pencil& recv = recv_by_member[me];
+    const int ndims = send.ndims;
+    HandleGeometry g;
+    g.ttype = ttype;
+    g.ndims = ndims;
+    g.comm_size = p;
+    g.comm_rank = me;
+    g.members = members;
+    for (int i = 0; i < 3; ++i) g.send_dims[i] = i < ndims ? send.counts[i] : 1, g.recv_dims[i] = i < ndims ? recv.counts[i] : 1;
+    const bool forward = ttype == T_X_TO_Y || ttype == T_Y_TO_Z || ttype == T_Z_TO_X;
+    int kernel_type = forward ? K_PERMUTE_FORWARD : K_PERMUTE_BACKWARD;  // :232-239
+    g.pack_kernel = kernel_type;
+    g.has_exchange = p > 1;
+    if (!g.has_exchange) return g;  // :246-253
+
+    // 1-based dimension accessors, as in the reference text
+    auto S = [&](int d, int r) { return send_by_member[r].counts[d - 1]; };
+    auto s = [&](int d, int r) { return send_by_member[r].starts[d - 1]; };
+    auto D = [&](int d, int r) { return recv_by_member[r].counts[d - 1]; };
+    auto dd = [&](int d, int r) { return recv_by_member[r].starts[d - 1]; };
+
+    // in%ln(:, i), in%ls(:, i) as computed by member `frm` (:295-336)
+    auto send_box = [&](int i, int frm, int64_t ln[3], int64_t ls[3]) {
+        ln[2] = 1, ls[2] = 0;
+        if (ndims == 2) {
+            ln[0] = D(2, i), ln[1] = S(2, frm);
+            ls[0] = dd(2, i), ls[1] = s(2, frm);
+        } else if (ttype == T_X_TO_Z) {
+            ln[0] = S(1, frm), ln[1] = D(3, i), ln[2] = S(3, frm);
+            ls[0] = s(1, frm), ls[1] = dd(3, i), ls[2] = s(3, frm);
+        } else if (ttype == T_Z_TO_X || ttype == T_X_TO_Y || ttype == T_Y_TO_Z) {
+            ln[0] = D(3, i), ln[1] = S(2, frm), ln[2] = S(3, frm);
+            ls[0] = dd(3, i), ls[1] = s(2, frm), ls[2] = s(3, frm);
+        } else {
+            ln[0] = D(2, i), ln[1] = S(2, frm), ln[2] = S(3, frm);
+            ls[0] = dd(2, i), ls[1] = s(2, frm), ls[2] = s(3, frm);
+        }
+    };
+
+    g.send_nd.assign(5 * (size_t)p, 0);
+    int64_t sdispl = 0;
+    for (int i = 0; i < p; ++i) {
+        int64_t ln[3], ls[3];
+        send_box(i, me, ln, ls);
+        int32_t* nd = &g.send_nd[5 * (size_t)i];
+        nd[3] = (int32_t)(ttype == T_X_TO_Z ? ln[0] * ls[1] : ls[0]);  // :337-341
+        nd[0] = (int32_t)ln[0], nd[1] = (int32_t)ln[1], nd[2] = ndims == 3 ? (int32_t)ln[2] : 1;
+        nd[4] = (int32_t)sdispl;  // :413
+        const int64_t cnt = ln[0] * ln[1] * (ndims == 3 ? ln[2] : 1);
+        g.send_counts.push_back(cnt);
+        g.send_displs.push_back(sdispl);
+        sdispl += cnt;
+    }
+
+    const bool two_step = (ttype == T_Y_TO_X || ttype == T_Z_TO_Y) && ndims == 3 && !fused;  // :430-433
+    if (two_step) kernel_type = K_PERMUTE_BACKWARD_START;
+    if (fused) {  // get_fused, abstract_kernel.F90:202-217
+        if (kernel_type == K_PERMUTE_FORWARD) kernel_type = K_PACK_FORWARD;
+        if (kernel_type == K_PERMUTE_BACKWARD) kernel_type = K_PACK_BACKWARD;
+    }
+    g.pack_kernel = kernel_type;
+    g.is_pipelined = pipelined || fused;
+    g.is_fused = fused;
+
+    g.recv_nd.assign(5 * (size_t)p, 0);
+    int64_t rdispl = 0;
+    for (int i = 0; i < p; ++i) {
+        int64_t lni[3], lsi[3];
+        send_box(me, i, lni, lsi);  // what member i announces it sends to me (:421-422, 488-489)
+        const int64_t recvsize = lni[0] * lni[1] * (ndims == 3 ? lni[2] : 1);
+        int64_t ln[3] = {0, 0, 0}, ls[3] = {0, 0, 0};
+        if (recvsize > 0) {  // :490-531
+            if (ndims == 2) {
+                ln[0] = S(2, i), ln[1] = D(2, me);
+                ls[0] = s(2, i), ls[1] = dd(2, me);
+            } else if (ttype == T_X_TO_Z) {
+                ln[0] = S(3, i), ln[1] = D(2, me), ln[2] = D(3, me);
+                ls[0] = s(3, i), ls[1] = dd(2, me), ls[2] = dd(3, me);
+            } else if (ttype == T_Z_TO_X) {
+                ln[0] = D(1, me), ln[1] = S(3, i), ln[2] = D(3, me);
+                ls[0] = dd(1, me), ls[1] = s(3, i), ls[2] = dd(3, me);
+            } else if (ttype == T_X_TO_Y || ttype == T_Y_TO_Z) {
+                ln[0] = S(2, i), ln[1] = D(2, me), ln[2] = D(3, me);
+                ls[0] = s(2, i), ls[1] = s(2, me), ls[2] = dd(3, me);
+            } else {
+                ln[0] = S(3, i), ln[1] = D(2, me), ln[2] = D(3, me);
+                ls[0] = s(3, i), ls[1] = s(2, me), ls[2] = dd(3, me);
+            }
+        }
+        int32_t* nd = &g.recv_nd[5 * (size_t)i];
+        nd[0] = (int32_t)ln[0], nd[1] = (int32_t)ln[1], nd[2] = ndims == 3 ? (int32_t)ln[2] : 1;
+        nd[3] = (int32_t)rdispl;                                                 // :582
+        nd[4] = (int32_t)(ttype == T_Z_TO_X ? ln[0] * ls[1] : ls[0]);           // :583-588
+        g.recv_counts.push_back(recvsize);
+        g.recv_displs.push_back(rdispl);
+        rdispl += recvsize;
+    }
+
+    int uk = K_UNPACK;  // :618-621
+    if (g.is_pipelined) uk = K_UNPACK_PIPELINED;
+    if (two_step) uk = K_PERMUTE_BACKWARD_END;
+    if (g.is_pipelined && two_step) uk = K_PERMUTE_BACKWARD_END_PIPELINED;
+    g.unpack_kernel = uk;
+    return g;
+}
+
+}  // namespace dtfftb

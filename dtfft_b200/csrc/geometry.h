@@ -1,0 +1,82 @@
+// Decomposition and per-peer block geometry (CUDA-free host logic).
+//
+// Restates the layout math the kernels are parameterised by:
+//   get_local_size            src/dtfft_pencil.F90:237-279
+//   pencil permutations        src/dtfft_transpose_plan.F90:1046-1082
+//   default grid choice        src/dtfft_transpose_plan.F90:170-203
+//   create_pencils_and_comm    src/dtfft_transpose_plan.F90:1084-1131
+//   1-D communicator of a transposition   src/dtfft_abstract_reshape_handle.F90:156-188
+//   neighbor_data / counts / displs / kernel kinds   src/dtfft_reshape_handle_generic.F90:291-640
+// MPI is replaced by a world allgather callback (comm.h); sub-communicators are index
+// lists into the world.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace dtfftb {
+
+enum TransposeType : int { T_X_TO_Y = 1, T_Y_TO_X = -1, T_Y_TO_Z = 2, T_Z_TO_Y = -2, T_X_TO_Z = 3, T_Z_TO_X = -3 };
+enum ReshapeType : int { R_X_BRICKS_TO_PENCILS = 11, R_X_PENCILS_TO_BRICKS = 12, R_Z_PENCILS_TO_BRICKS = 13, R_Z_BRICKS_TO_PENCILS = 14 };
+
+constexpr int kDefTileSize = 32;  // DEF_TILE_SIZE, src/dtfft_parameters.F90 (Z-slab rule on CUDA)
+
+struct Pencil {
+    int aligned_dim = 0;  // 1-based like the reference
+    int ndims = 0;
+    int32_t starts[3] = {0, 0, 0};
+    int32_t counts[3] = {1, 1, 1};
+    bool is_even = true;
+    bool is_distributed = false;
+    long long size() const {
+        long long s = 1;
+        for (int i = 0; i < ndims; ++i) s *= counts[i];
+        return s;
+    }
+};
+
+void local_size(int n_global, int comm_dim, int comm_rank, int32_t* start, int32_t* count);
+// MPI_Dims_create for the shapes dtFFT asks for (zeros are free entries).
+void dims_create(int nnodes, int ndims, int32_t* dims);
+
+struct GridChoice {
+    int32_t comm_dims[3] = {1, 1, 1};
+    bool is_z_slab = false, is_y_slab = false;
+    bool invalid_grid = false;
+};
+GridChoice choose_grid(int ndims, const int32_t* dims, int comm_size, bool cuda, bool z_slab_enabled,
+                       bool y_slab_enabled);
+
+void cart_coords(int rank, int ndims, const int32_t* comm_dims, int32_t* coords);
+int cart_rank(int ndims, const int32_t* comm_dims, const int32_t* coords);
+// Global ranks of 1-D communicator `comm_id` (1 = whole grid, d >= 2 = grid dimension d) containing `rank`.
+std::vector<int> comm_members(int rank, int ndims, const int32_t* comm_dims, int comm_id);
+// dperm[d][j]: global axis of local axis j of pencil d; cperm[d][j]: grid dimension splitting it (0-based).
+void permutations(int ndims, int dperm[3][3], int cperm[3][3]);
+// The ndims pencils of `rank` for the default (no user pencil) decomposition.
+void make_pencils(int ndims, const int32_t* dims, const int32_t* comm_dims, int rank, Pencil out[3]);
+
+int transpose_comm_id(int ttype);
+void transpose_pencil_ids(int ttype, int* send, int* recv);  // 0-based pencil indices
+
+struct HandleGeometry {
+    int ttype = 0;            // dtfft_transpose_t value, 0 for reshapes
+    int rtype = 0;            // dtfft_reshape_t value, 0 for transposes
+    int ndims = 0;
+    int comm_size = 1, comm_rank = 0;
+    std::vector<int> members;  // global ranks of the 1-D communicator
+    int32_t send_dims[3] = {1, 1, 1}, recv_dims[3] = {1, 1, 1};
+    int pack_kernel = -1, unpack_kernel = -1;  // kernel_type_t values (-1 = dummy / none)
+    std::vector<int32_t> send_nd, recv_nd;     // 5 x P, row per peer
+    std::vector<int64_t> send_counts, send_displs, recv_counts, recv_displs;  // elements
+    bool has_exchange = false, is_pipelined = false, is_fused = false;
+    bool is_pack_free = false, is_unpack_free = false;
+    int reshape_strat = 0;
+};
+
+// Geometry of transposition `ttype` for member `me` of a 1-D communicator whose members'
+// send / recv pencils are given in sub-communicator order.
+HandleGeometry transpose_geometry(int ttype, const std::vector<Pencil>& send_by_member,
+                                  const std::vector<Pencil>& recv_by_member, int me, const std::vector<int>& members,
+                                  bool pipelined, bool fused);
+
+}  // namespace dtfftb

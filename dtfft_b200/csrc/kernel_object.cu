@@ -329,8 +329,11 @@ int Kernel::rebuild_tables() {
     if (d_blocks_) cudaFree(d_blocks_);
     d_blocks_ = nullptr;
     std::vector<BlockDesc> host;
-    int grid_mult = 4;  // CTAs per resident slot: >1 lets the hardware scheduler even out the tail
-    if (const char* e = getenv("DTFFTB_GRID_MULT")) grid_mult = std::max(1, atoi(e));
+    // CTAs per resident slot.  Measured on B200 (profiles/r01_kbench.md): a static persistent
+    // partition (1) loses ~7 % to SMs that finish early; one CTA per tile (0 = no cap, the
+    // default) lets the hardware scheduler balance the tail and is the fastest setting.
+    int grid_mult = 0;
+    if (const char* e = getenv("DTFFTB_GRID_MULT")) grid_mult = std::max(0, atoi(e));
 
     auto make_desc = [&](const Box& b, int t0, int t1, long long begin, int peer) {
         BlockDesc d{};
@@ -374,7 +377,7 @@ int Kernel::rebuild_tables() {
         const int threads = 32 * tile_.rows;
         const size_t smem = (size_t)TA * (TB + 1) * es_;
         int per_sm = std::min({2048 / threads, (int)((227 * 1024) / (smem + 1024)), 32});
-        grid_cap_ = sm_count_ * std::max(1, per_sm) * grid_mult;
+        grid_cap_ = grid_mult ? sm_count_ * std::max(1, per_sm) * grid_mult : 0x7fffffff;
     } else if (family_ == FAM_R) {
         // widest unit allowed by the geometry
         std::vector<Box> norm = boxes_;
@@ -448,7 +451,7 @@ int Kernel::rebuild_tables() {
             }
             if (unit == unit_geo_) tx_ = tx;
         }
-        grid_cap_ = sm_count_ * 8 * grid_mult;
+        grid_cap_ = grid_mult ? sm_count_ * 8 * grid_mult : 0x7fffffff;
     }
     if (!host.empty()) {
         cudaError_t ce = cudaMalloc(&d_blocks_, host.size() * sizeof(BlockDesc));

@@ -61,7 +61,7 @@ __device__ __forceinline__ ItemPos decode_item(const BlockDesc& d, long long ite
 // Family T
 // ---------------------------------------------------------------------------------
 template <typename T, int KA, int KB, int ROWS>
-__global__ void __launch_bounds__(32 * ROWS)
+__global__ void __launch_bounds__(32 * ROWS, (ROWS <= 4 ? 4 : ROWS <= 8 ? 3 : 1))
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
                            int nblocks, long long total_items) {
     constexpr int TA = 32 * KA, TB = 32 * KB;
@@ -122,6 +122,8 @@ cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nbl
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
+            // let three 66.5 KB tiles share an SM
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr_set = true;
         }
     }
