@@ -61,7 +61,7 @@ __device__ __forceinline__ ItemPos decode_item(const BlockDesc& d, long long ite
 // Family T
 // ---------------------------------------------------------------------------------
 template <typename T, int KA, int KB, int ROWS>
-__global__ void __launch_bounds__(32 * ROWS, (ROWS <= 4 ? 4 : ROWS <= 8 ? 3 : 1))
+__global__ void __launch_bounds__(32 * ROWS)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
                            int nblocks, long long total_items) {
     constexpr int TA = 32 * KA, TB = 32 * KB;
