@@ -57,8 +57,68 @@ def lib() -> C.CDLL:
                  "dtfftb_kernel_set_peer_out", "dtfftb_kernel_destroy", "dtfftb_kernel_get_info",
                  "dtfftb_kernel_set_tile", "dtfftb_kernel_autotune"):
         getattr(L, name).restype = C.c_int
+    _declare_plan_api(L)
     _lib = L
     return L
+
+
+def _declare_plan_api(L):
+    """argtypes / restypes of include/dtfft_b200_api.h (pointers must not be truncated to int)."""
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
+    szp = C.POINTER(C.c_size_t)
+    pvp = C.POINTER(vp)
+    intp = C.POINTER(C.c_int)
+    sig = {
+        "dtfft_create_plan_c2c": [C.c_int8, i32p, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_create_plan_r2c": [C.c_int8, i32p, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_create_plan_r2r": [C.c_int8, i32p, intp, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_create_plan_c2c_pencil": [vp, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_create_plan_r2c_pencil": [vp, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_create_plan_r2r_pencil": [vp, intp, vp, C.c_int, C.c_int, C.c_int, pvp],
+        "dtfft_execute": [vp, vp, vp, C.c_int, vp],
+        "dtfft_transpose": [vp, vp, vp, C.c_int, vp],
+        "dtfft_reshape": [vp, vp, vp, C.c_int, vp],
+        "dtfft_transpose_start": [vp, vp, vp, C.c_int, vp, pvp],
+        "dtfft_reshape_start": [vp, vp, vp, C.c_int, vp, pvp],
+        "dtfft_transpose_end": [vp, vp],
+        "dtfft_reshape_end": [vp, vp],
+        "dtfft_destroy": [pvp],
+        "dtfft_get_local_sizes": [vp, i32p, i32p, i32p, i32p, szp],
+        "dtfft_get_pencil": [vp, C.c_int, vp],
+        "dtfft_mem_alloc": [vp, C.c_size_t, pvp],
+        "dtfft_mem_free": [vp, vp],
+        "dtfft_report": [vp],
+        "dtfft_get_dims": [vp, C.POINTER(C.c_int8), C.POINTER(i32p)],
+        "dtfft_get_grid_dims": [vp, C.POINTER(C.c_int8), C.POINTER(i32p)],
+        "dtfft_get_stream": [vp, pvp],
+        "dtfft_get_backend_pipelined": [C.c_int, C.POINTER(C.c_bool)],
+        "dtfft_create_config": [vp],
+        "dtfft_set_config": [vp],
+        "dtfftb_plan_register_buffer": [vp, vp, C.c_size_t],
+        "dtfftb_plan_unregister_buffer": [vp, vp],
+        "dtfftb_plan_get_stats": [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+        "dtfftb_plan_peer_error": [vp],
+        "dtfftb_plan_create_dry": [C.c_int, C.c_int8, i32p, vp, vp, C.c_int, C.c_int, pvp],
+        "dtfftb_plan_describe_exchange": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p,
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
+    }
+    for name in ("alloc_size", "alloc_bytes", "element_size", "aux_size", "aux_bytes", "aux_size_transpose",
+                 "aux_bytes_transpose", "aux_size_reshape", "aux_bytes_reshape"):
+        sig[f"dtfft_get_{name}"] = [vp, szp]
+    for name in ("z_slab_enabled", "y_slab_enabled"):
+        sig[f"dtfft_get_{name}"] = [vp, C.POINTER(C.c_bool)]
+    for name in ("executor", "precision", "backend", "reshape_backend", "platform"):
+        sig[f"dtfft_get_{name}"] = [vp, intp]
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name in ("dtfft_get_error_string", "dtfft_get_precision_string", "dtfft_get_executor_string",
+                 "dtfft_get_backend_string"):
+        fn = getattr(L, name)
+        fn.argtypes = [C.c_int]
+        fn.restype = C.c_char_p
+    L.dtfft_get_version.restype = C.c_int32
 
 
 def check(code: int, where: str) -> None:

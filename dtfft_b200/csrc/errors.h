@@ -1,66 +1,13 @@
-// dtfft_error_t values used on this path (reference: include/dtfft_config.h.in:82-151)
-// and the mapping of CUDA / NCCL failures to return codes.
+// dtfft_error_t values (reference: include/dtfft_config.h.in:82-151) come from the public
+// header; this file adds the mapping of CUDA failures to return codes.
 #pragma once
 #include <cuda_runtime.h>
 
-#include "../../include/dtfft_b200.h"
+#include "../../include/dtfft_b200_api.h"
 
-enum {
-    DTFFT_SUCCESS = 0,
-    DTFFT_ERROR_PLAN_NOT_CREATED = 1,
-    DTFFT_ERROR_INVALID_TRANSPOSE_TYPE = 2,
-    DTFFT_ERROR_INVALID_N_DIMENSIONS = 3,
-    DTFFT_ERROR_INVALID_DIMENSION_SIZE = 4,
-    DTFFT_ERROR_INVALID_COMM_TYPE = 5,
-    DTFFT_ERROR_INVALID_PRECISION = 6,
-    DTFFT_ERROR_INVALID_EFFORT_FLAG = 7,
-    DTFFT_ERROR_INVALID_EXECUTOR_TYPE = 8,
-    DTFFT_ERROR_INVALID_COMM_DIMS = 9,
-    DTFFT_ERROR_INVALID_COMM_FAST_DIM = 10,
-    DTFFT_ERROR_MISSING_R2R_KINDS = 11,
-    DTFFT_ERROR_INVALID_R2R_KINDS = 12,
-    DTFFT_ERROR_R2C_TRANSPOSE_PLAN = 13,
-    DTFFT_ERROR_INPLACE_TRANSPOSE = 14,
-    DTFFT_ERROR_INVALID_AUX = 15,
-    DTFFT_ERROR_INVALID_LAYOUT = 16,
-    DTFFT_ERROR_INVALID_USAGE = 17,
-    DTFFT_ERROR_PLAN_IS_CREATED = 18,
-    DTFFT_ERROR_ALLOC_FAILED = 19,
-    DTFFT_ERROR_FREE_FAILED = 20,
-    DTFFT_ERROR_INVALID_ALLOC_BYTES = 21,
-    DTFFT_ERROR_PENCIL_ARRAYS_SIZE_MISMATCH = 25,
-    DTFFT_ERROR_PENCIL_ARRAYS_INVALID_SIZES = 26,
-    DTFFT_ERROR_PENCIL_INVALID_COUNTS = 27,
-    DTFFT_ERROR_PENCIL_INVALID_STARTS = 28,
-    DTFFT_ERROR_PENCIL_SHAPE_MISMATCH = 29,
-    DTFFT_ERROR_PENCIL_OVERLAP = 30,
-    DTFFT_ERROR_PENCIL_NOT_CONTINUOUS = 31,
-    DTFFT_ERROR_PENCIL_NOT_INITIALIZED = 32,
-    DTFFT_ERROR_INVALID_MEASURE_WARMUP_ITERS = 33,
-    DTFFT_ERROR_INVALID_MEASURE_ITERS = 34,
-    DTFFT_ERROR_INVALID_REQUEST = 35,
-    DTFFT_ERROR_TRANSPOSE_ACTIVE = 36,
-    DTFFT_ERROR_TRANSPOSE_NOT_ACTIVE = 37,
-    DTFFT_ERROR_INVALID_RESHAPE_TYPE = 38,
-    DTFFT_ERROR_RESHAPE_ACTIVE = 39,
-    DTFFT_ERROR_RESHAPE_NOT_ACTIVE = 40,
-    DTFFT_ERROR_INPLACE_RESHAPE = 41,
-    DTFFT_ERROR_INVALID_EXECUTE_TYPE = 43,
-    DTFFT_ERROR_RESHAPE_NOT_SUPPORTED = 44,
-    DTFFT_ERROR_R2C_EXECUTE_CALLED = 45,
-    DTFFT_ERROR_INVALID_CART_COMM = 46,
-    DTFFT_ERROR_INVALID_TRANSPOSE_MODE = 47,
-    DTFFT_ERROR_INVALID_ACCESS_MODE = 48,
-    DTFFT_ERROR_R2R_FFT_NOT_SUPPORTED = 101,
-    DTFFT_ERROR_GPU_INVALID_STREAM = 201,
-    DTFFT_ERROR_INVALID_BACKEND = 202,
-    DTFFT_ERROR_GPU_NOT_SET = 203,
-    DTFFT_ERROR_BACKENDS_DISABLED = 205,
-    DTFFT_ERROR_NOT_DEVICE_PTR = 300,
-    DTFFT_ERROR_INVALID_PLATFORM = 400,
-    DTFFT_ERROR_INVALID_PLATFORM_EXECUTOR = 401,
-    DTFFT_ERROR_INVALID_PLATFORM_BACKEND = 402,
-};
+// names used by the Fortran side of the reference (CONF_ macros) that differ from the C enum
+#define DTFFT_ERROR_INVALID_EFFORT_FLAG DTFFT_ERROR_INVALID_EFFORT
+#define DTFFT_ERROR_INVALID_EXECUTOR_TYPE DTFFT_ERROR_INVALID_EXECUTOR
 
 namespace dtfftb {
 inline int cuda_error(cudaError_t e) { return e == cudaSuccess ? 0 : DTFFTB_ERROR_CUDA_BASE - (int)e; }

@@ -2,6 +2,7 @@
 // Pure host code; compiled by nvcc only to keep one toolchain for the library.
 #include "geometry.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -267,6 +268,98 @@ HandleGeometry transpose_geometry(int ttype, const std::vector<Pencil>& send_by_
     if (g.is_pipelined && two_step) uk = K_PERMUTE_BACKWARD_END_PIPELINED;
     g.unpack_kernel = uk;
     return g;
+}
+
+RankLayout layout_of(const Pencil& p) {
+    RankLayout l;
+    l.ndims = p.ndims;
+    int dperm[3][3], cperm[3][3];
+    permutations(p.ndims, dperm, cperm);
+    for (int j = 0; j < p.ndims; ++j) {
+        l.axis[j] = dperm[p.aligned_dim - 1][j];
+        l.starts[j] = p.starts[j];
+        l.counts[j] = p.counts[j];
+    }
+    return l;
+}
+
+namespace {
+struct AxisView {
+    long long lo[3], n[3];          // per GLOBAL axis: intersection start / extent
+    long long sstride[3], dstride[3];  // per GLOBAL axis: stride in src / dst
+    long long sstart[3], dstart[3];
+    bool empty = false;
+};
+
+AxisView view_of(const RankLayout& src, const RankLayout& dst) {
+    AxisView v{};
+    const int nd = src.ndims;
+    long long st = 1;
+    for (int j = 0; j < nd; ++j) {
+        v.sstride[src.axis[j]] = st, v.sstart[src.axis[j]] = src.starts[j];
+        st *= src.counts[j];
+    }
+    st = 1;
+    for (int j = 0; j < nd; ++j) {
+        v.dstride[dst.axis[j]] = st, v.dstart[dst.axis[j]] = dst.starts[j];
+        st *= dst.counts[j];
+    }
+    for (int js = 0; js < nd; ++js) {
+        const int A = src.axis[js];
+        int jd = 0;
+        while (dst.axis[jd] != A) ++jd;
+        const long long lo = std::max<long long>(src.starts[js], dst.starts[jd]);
+        const long long hi = std::min<long long>((long long)src.starts[js] + src.counts[js],
+                                                 (long long)dst.starts[jd] + dst.counts[jd]);
+        v.lo[A] = lo, v.n[A] = hi - lo;
+        if (hi <= lo) v.empty = true;
+    }
+    return v;
+}
+}  // namespace
+
+Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposing) {
+    const int nd = src.ndims;
+    const AxisView v = view_of(src, dst);
+    const int a = src.axis[0], b = dst.axis[0];
+    if (transposing) *transposing = a != b;
+    Box x;
+    if (v.empty) {
+        x.n0 = 0;
+        return x;
+    }
+    for (int j = 0; j < nd; ++j) {
+        const int A = src.axis[j];
+        x.in_off += (v.lo[A] - v.sstart[A]) * v.sstride[A];
+        x.out_off += (v.lo[A] - v.dstart[A]) * v.dstride[A];
+    }
+    if (a != b) {  // family T: axes (a, b, c)
+        int c = -1;
+        for (int j = 0; j < nd; ++j)
+            if (src.axis[j] != a && src.axis[j] != b) c = src.axis[j];
+        x.n0 = v.n[a], x.n1 = v.n[b], x.n2 = c >= 0 ? v.n[c] : 1;
+        x.is1 = v.sstride[b], x.is2 = c >= 0 ? v.sstride[c] : 0;
+        x.os0 = v.dstride[a], x.os1 = 1, x.os2 = c >= 0 ? v.dstride[c] : 0;
+    } else {  // family R: axes in source order
+        const int A1 = src.axis[1], A2 = nd == 3 ? src.axis[2] : -1;
+        x.n0 = v.n[a], x.n1 = v.n[A1], x.n2 = A2 >= 0 ? v.n[A2] : 1;
+        x.is1 = v.sstride[A1], x.is2 = A2 >= 0 ? v.sstride[A2] : 0;
+        x.os0 = 1, x.os1 = v.dstride[A1], x.os2 = A2 >= 0 ? v.dstride[A2] : 0;
+    }
+    return x;
+}
+
+RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like) {
+    const AxisView v = view_of(src, dst);
+    RankLayout s;
+    s.ndims = src.ndims;
+    for (int j = 0; j < s.ndims; ++j) {
+        const int A = order_like.axis[j];
+        s.axis[j] = A;
+        s.starts[j] = (int32_t)v.lo[A];
+        s.counts[j] = v.empty ? 0 : (int32_t)v.n[A];
+    }
+    return s;
 }
 
 }  // namespace dtfftb

@@ -79,4 +79,28 @@ HandleGeometry transpose_geometry(int ttype, const std::vector<Pencil>& send_by_
                                   const std::vector<Pencil>& recv_by_member, int me, const std::vector<int>& members,
                                   bool pipelined, bool fused);
 
+// ---- geometry from global-index intersections (fused NVLink path, brick reshapes) ----
+// A rank's local array: local axis j is global axis `axis[j]`, holding global indices
+// [starts[j], starts[j] + counts[j]); column-major with local axis 0 fastest.
+struct RankLayout {
+    int ndims = 0;
+    int axis[3] = {0, 1, 2};
+    int32_t starts[3] = {0, 0, 0};
+    int32_t counts[3] = {1, 1, 1};
+    long long volume() const {
+        long long v = 1;
+        for (int j = 0; j < ndims; ++j) v *= counts[j];
+        return v;
+    }
+};
+RankLayout layout_of(const Pencil& p);
+struct Box;  // kernel_object.h
+// The part of `src` that lands in `dst`, as a strided box: element (global g) is read at
+// in_off + sum_j (g - src.start) * src.stride and written at out_off + ... of dst.
+// *transposing = the fastest axes differ (family T), else family R.
+Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposing);
+// Layout of the contiguous slot that carries the (src -> dst) block between two ranks:
+// the intersection, stored in the axis order of `order_like`.
+RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like);
+
 }  // namespace dtfftb

@@ -1,0 +1,195 @@
+// ReshapeHandle (see handle.h for the reference citations).
+#include "handle.h"
+
+#include <algorithm>
+
+#include "errors.h"
+
+namespace dtfftb {
+
+void ReshapeHandle::destroy() {
+    fused_.clear();
+    fused_boxes_.clear();
+    nccl_.reset();
+    pack_.reset();
+    unpack_.reset();
+    created_ = false;
+}
+
+int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int comm_id, const std::vector<int>& members,
+                          int me, const std::vector<Pencil>& send_by_member, const std::vector<Pencil>& recv_by_member,
+                          int64_t base_storage, int backend) {
+    destroy();
+    ctx_ = ctx;
+    is_transpose_ = ttype != 0;
+    comm_id_ = comm_id;
+    members_ = members;
+    me_ = me;
+    es_ = base_storage;
+    backend_ = backend;
+    const int P = (int)members.size();
+    has_exchange_ = P > 1;
+    aux_bytes_ = 0;
+    const Pencil& send = send_by_member[(size_t)me];
+    const Pencil& recv = recv_by_member[(size_t)me];
+    const int ndims = send.ndims;
+    send_elems_ = send.size();
+    recv_elems_ = recv.size();
+    int rc;
+
+    // element counts that cross the NVLink fabric (everything not addressed to myself)
+    {
+        const RankLayout src = layout_of(send);
+        long long self = 0;
+        bool tr = false;
+        Box b = intersect_box(src, layout_of(recv), &tr);
+        if (!b.empty()) self = b.volume();
+        remote_elems_ = send_elems_ - self;
+    }
+
+    if (!has_exchange_) {  // reshape_handle_generic.F90:246-253
+        pack_.reset(new Kernel);
+        geo_ = HandleGeometry{};
+        geo_.ttype = ttype, geo_.rtype = rtype, geo_.ndims = ndims;
+        int kt = K_COPY;
+        if (is_transpose_) {
+            const bool fwd = ttype == T_X_TO_Y || ttype == T_Y_TO_Z || ttype == T_Z_TO_X;
+            kt = fwd ? K_PERMUTE_FORWARD : K_PERMUTE_BACKWARD;
+        }
+        geo_.pack_kernel = kt;
+        rc = pack_->create(ndims, send.counts, kt, es_, nullptr, 0, ctx_.effort, false);
+        if (rc) return rc;
+        launches_ = kt == K_COPY ? 0 : 1;
+        created_ = true;
+        return DTFFT_SUCCESS;
+    }
+
+    if (backend_ == BACKEND_NVLINK_FUSED) {
+        if (!ctx_.peers || !ctx_.peers->available()) return DTFFT_ERROR_INVALID_BACKEND;
+        const RankLayout src = layout_of(send);
+        fused_boxes_.assign((size_t)P, Box{});
+        bool any_t = false, any_r = false;
+        for (int i = 0; i < P; ++i) {
+            bool tr = false;
+            Box b = intersect_box(src, layout_of(recv_by_member[(size_t)i]), &tr);
+            fused_boxes_[(size_t)i] = b;
+            if (!b.empty()) (tr ? any_t : any_r) = true;
+        }
+        if (any_t && any_r) return DTFFTB_ERROR_INTERNAL;
+        fused_family_ = any_r ? FAM_R : FAM_T;
+        geo_ = HandleGeometry{};
+        geo_.ttype = ttype, geo_.rtype = rtype, geo_.ndims = ndims;
+        geo_.comm_size = P, geo_.comm_rank = me, geo_.members = members;
+        geo_.has_exchange = true, geo_.is_fused = true;
+        launches_ = 3;  // barrier + fused kernel + barrier
+        created_ = true;
+        return DTFFT_SUCCESS;
+    }
+
+    if (backend_ != BACKEND_NCCL && backend_ != BACKEND_NCCL_PIPELINED) return DTFFT_ERROR_INVALID_BACKEND;
+    if (!ctx_.nccl) return DTFFTB_ERROR_INTERNAL;
+    const bool pipelined = backend_is_pipelined(backend_);
+    pack_.reset(new Kernel);
+    unpack_.reset(new Kernel);
+    nccl_.reset(new NcclBackend);
+
+    if (is_transpose_) {
+        geo_ = transpose_geometry(ttype, send_by_member, recv_by_member, me, members, pipelined, false);
+        rc = pack_->create(ndims, geo_.send_dims, geo_.pack_kernel, es_, geo_.send_nd.data(), P, ctx_.effort, false);
+        if (rc) return rc;
+        rc = unpack_->create(ndims, geo_.recv_dims, geo_.unpack_kernel, es_, geo_.recv_nd.data(), P, ctx_.effort, false);
+        if (rc) return rc;
+    } else {
+        // brick <-> pencil reshape: same axis order on both sides; block (me -> i) is the
+        // global-index intersection, carried in a contiguous slot in destination order
+        geo_ = HandleGeometry{};
+        geo_.ttype = 0, geo_.rtype = rtype, geo_.ndims = ndims;
+        geo_.comm_size = P, geo_.comm_rank = me, geo_.members = members;
+        geo_.has_exchange = true, geo_.is_pipelined = pipelined;
+        geo_.pack_kernel = pipelined ? K_PACK_PIPELINED : K_PACK;
+        geo_.unpack_kernel = pipelined ? K_UNPACK_PIPELINED : K_UNPACK;
+        for (int j = 0; j < 3; ++j) geo_.send_dims[j] = j < ndims ? send.counts[j] : 1, geo_.recv_dims[j] = j < ndims ? recv.counts[j] : 1;
+        const RankLayout src = layout_of(send), dst = layout_of(recv);
+        std::vector<Box> pack_boxes((size_t)P), unpack_boxes((size_t)P);
+        int64_t sdispl = 0, rdispl = 0;
+        for (int i = 0; i < P; ++i) {
+            bool tr = false;
+            const RankLayout peer_dst = layout_of(recv_by_member[(size_t)i]);
+            RankLayout slot = slot_layout(src, peer_dst, peer_dst);
+            Box pb = intersect_box(src, slot, &tr);
+            pb.out_off += sdispl;
+            pack_boxes[(size_t)i] = pb;
+            const int64_t cnt = pb.empty() ? 0 : pb.volume();
+            geo_.send_counts.push_back(cnt), geo_.send_displs.push_back(sdispl);
+            sdispl += cnt;
+
+            const RankLayout peer_src = layout_of(send_by_member[(size_t)i]);
+            RankLayout rslot = slot_layout(peer_src, dst, dst);
+            Box ub = intersect_box(rslot, dst, &tr);
+            ub.in_off += rdispl;
+            unpack_boxes[(size_t)i] = ub;
+            const int64_t rcnt = ub.empty() ? 0 : ub.volume();
+            geo_.recv_counts.push_back(rcnt), geo_.recv_displs.push_back(rdispl);
+            rdispl += rcnt;
+        }
+        rc = pack_->create_boxes(FAM_R, es_, pack_boxes);
+        if (rc) return rc;
+        rc = unpack_->create_boxes(FAM_R, es_, unpack_boxes);
+        if (rc) return rc;
+    }
+    std::vector<int> mapping = members;  // NCCL communicator spans the world: member -> world rank
+    rc = nccl_->create(backend_, ctx_.nccl, me, mapping, geo_.send_displs, geo_.send_counts, geo_.recv_displs,
+                       geo_.recv_counts, es_);
+    if (rc) return rc;
+    if (pipelined) nccl_->set_unpack_kernel(unpack_.get());
+    aux_bytes_ = nccl_->aux_bytes();
+    launches_ = pipelined ? 1 + P : 2;
+    created_ = true;
+    return DTFFT_SUCCESS;
+}
+
+int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
+    PeerRegistry& peers = *ctx_.peers;
+    const int P = (int)members_.size();
+    int slot = -1;
+    size_t off = 0;
+    if (!peers.resolve(out, (size_t)(recv_elems_ * es_), &slot, &off)) return DTFFTB_ERROR_NOT_REGISTERED;
+    auto it = fused_.find(out);
+    if (it == fused_.end()) {
+        std::unique_ptr<Kernel> k(new Kernel);
+        int rc = k->create_boxes(fused_family_, es_, fused_boxes_);
+        if (rc) return rc;
+        std::vector<void*> bases((size_t)P);
+        for (int i = 0; i < P; ++i) bases[(size_t)i] = i == me_ ? out : peers.peer_ptr(members_[(size_t)i], slot, off);
+        rc = k->set_peer_out(bases.data(), nullptr);
+        if (rc) return rc;
+        if (fused_.size() > 16) fused_.clear();
+        it = fused_.emplace(out, std::move(k)).first;
+    }
+    // channel: one pair per 1-D communicator id
+    int rc = peers.barrier(members_, 2 * (comm_id_ - 1), stream);  // every member's `out` is free
+    if (rc) return rc;
+    rc = it->second->execute_all(in, out, stream);
+    if (rc) return rc;
+    return peers.barrier(members_, 2 * (comm_id_ - 1) + 1, stream);  // every block has landed
+}
+
+int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {
+    if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
+    if (!has_exchange_) return pack_->execute(in, out, stream, 0, false);
+    if (backend_ == BACKEND_NVLINK_FUSED) return execute_fused(in, out, stream);
+    int rc;
+    if (nccl_->is_pipelined()) {  // reshape_handle_generic.F90:723-730
+        if (!aux) return DTFFT_ERROR_INVALID_AUX;
+        rc = pack_->execute_all(in, aux, stream);  // in -> aux   pack
+        if (rc) return rc;
+        return nccl_->execute(aux, out, stream, in);  // aux -> in exchange, in -> out unpack
+    }
+    rc = pack_->execute_all(in, out, stream);  // :752  in -> out  pack
+    if (rc) return rc;
+    rc = nccl_->execute(out, in, stream, aux);  // :755  out -> in  exchange
+    if (rc) return rc;
+    return unpack_->execute_all(in, out, stream);  // :758  in -> out  unpack
+}
+
+}  // namespace dtfftb

@@ -1,0 +1,75 @@
+// One transposition / reshape between two decompositions: the B200 replacement of
+// reshape_handle_generic (src/dtfft_reshape_handle_generic.F90:174-777).
+//
+// Three execution shapes:
+//   * no exchange (1 rank in the 1-D communicator): a single local permute / copy (:246-253);
+//   * NCCL / NCCL_PIPELINED: pack -> all-to-all(v) -> unpack with the reference's buffer
+//     choreography (:695-759); transposes use the reference's neighbor_data geometry
+//     (geometry.cu), brick reshapes use global-index intersections;
+//   * NVLINK_FUSED: ONE kernel reads the local array and stores every element at its final
+//     position in the owning peer's `out` through NVLink peer mappings, bracketed by two
+//     device barriers -- pack, exchange and unpack of the reference collapse into one pass
+//     (1 HBM read + 1 remote/local write per element instead of 3 + 3).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "backend.h"
+#include "comm.h"
+#include "geometry.h"
+#include "kernel_object.h"
+#include "peer.h"
+
+namespace dtfftb {
+
+struct HandleContext {
+    ncclComm_t nccl = nullptr;      // communicator over the whole process grid (may be null when P == 1)
+    PeerRegistry* peers = nullptr;  // symmetric-buffer registry (NVLINK_FUSED)
+    int effort = 0;
+};
+
+class ReshapeHandle {
+public:
+    ~ReshapeHandle() { destroy(); }
+    // `send_by_member[i]` / `recv_by_member[i]`: source / destination layout of member i of the
+    // 1-D communicator `members` (world ranks); `me` = my index in it.  `ttype` != 0 for a
+    // transposition (dtfft_transpose_t), else `rtype` (dtfft_reshape_t).
+    int create(const HandleContext& ctx, int ttype, int rtype, int comm_id, const std::vector<int>& members, int me,
+               const std::vector<Pencil>& send_by_member, const std::vector<Pencil>& recv_by_member,
+               int64_t base_storage, int backend);
+    int execute(void* in, void* out, cudaStream_t stream, void* aux);
+    int64_t aux_bytes() const { return aux_bytes_; }
+    bool aux_needed() const { return aux_bytes_ > 0; }
+    int backend() const { return backend_; }
+    bool has_exchange() const { return has_exchange_; }
+    // Algorithmic payload of one execute on this rank: elements moved, and those that leave the GPU.
+    long long local_elements() const { return send_elems_; }
+    long long remote_elements() const { return remote_elems_; }
+    int kernel_launches() const { return launches_; }  // of OUR kernels per execute
+    const HandleGeometry& geometry() const { return geo_; }
+    void destroy();
+
+private:
+    int execute_fused(void* in, void* out, cudaStream_t stream);
+
+    HandleContext ctx_;
+    bool created_ = false, has_exchange_ = false, is_transpose_ = true;
+    int backend_ = BACKEND_NCCL, comm_id_ = 1, me_ = 0;
+    int64_t es_ = 0, aux_bytes_ = 0;
+    long long send_elems_ = 0, remote_elems_ = 0, recv_elems_ = 0;
+    int launches_ = 0;
+    std::vector<int> members_;
+    HandleGeometry geo_;
+    std::unique_ptr<Kernel> pack_, unpack_;
+    std::unique_ptr<NcclBackend> nccl_;
+    // fused path
+    std::vector<Box> fused_boxes_;  // per member, out_off relative to the member's `out`
+    Family fused_family_ = FAM_NONE;
+    std::map<const void*, std::unique_ptr<Kernel>> fused_;  // keyed by my `out` pointer
+};
+
+}  // namespace dtfftb

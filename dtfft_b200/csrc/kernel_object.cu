@@ -220,6 +220,7 @@ void Kernel::destroy() {
     d_blocks_ = nullptr;
     created_ = false;
     noop_ = true;
+    custom_ = false;
     nd_.clear();
     boxes_.clear();
     peer_out_.clear();
@@ -323,6 +324,38 @@ int Kernel::create(int ndims, const int32_t* dims, int kernel_type, int64_t base
         cudaGetLastError();
     }
     return DTFFT_SUCCESS;
+}
+
+int Kernel::create_boxes(Family family, int64_t base_storage, const std::vector<Box>& boxes) {
+    destroy();
+    if (family != FAM_T && family != FAM_R) return DTFFTB_ERROR_INTERNAL;
+    if (base_storage != 4 && base_storage != 8 && base_storage != 16) return DTFFTB_ERROR_INTERNAL;
+    es_ = base_storage;
+    ndims_ = 3;
+    created_ = true;
+    custom_ = true;
+    family_ = family;
+    type_ = family == FAM_T ? K_PACK_FORWARD : K_PACK_PIPELINED;  // per-peer kinds: execute(n) = one peer, execute_all = every peer
+    P_ = (int)boxes.size();
+    boxes_ = boxes;
+    bool any = false;
+    for (auto& b : boxes_) any |= !b.empty();
+    noop_ = !any;
+    if (noop_) return DTFFT_SUCCESS;
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    if (family_ == FAM_T) {
+        tile_ = TileCfg{2, 2, 8};
+        if (const char* e = getenv("DTFFTB_TILE")) {
+            int ka, kb, r;
+            if (sscanf(e, "%d,%d,%d", &ka, &kb, &r) == 3 && transpose_cfg_supported((int)es_, TileCfg{ka, kb, r}))
+                tile_ = TileCfg{ka, kb, r};
+        }
+    }
+    return rebuild_tables();
 }
 
 int Kernel::rebuild_tables() {
@@ -557,7 +590,8 @@ int Kernel::set_peer_out(void* const* out_bases, const int64_t* out_displs_overr
     peer_out_.clear();
     peer_out_displ_.clear();
     const int ptype = per_neighbor_type(type_);
-    for (int n = 0; n < P_; ++n) boxes_[n] = make_box(ptype, ndims_, dims_, &nd_[5 * (size_t)n]);
+    if (!custom_)
+        for (int n = 0; n < P_; ++n) boxes_[n] = make_box(ptype, ndims_, dims_, &nd_[5 * (size_t)n]);
     if (out_bases) {
         peer_out_.assign(out_bases, out_bases + P_);
         if (out_displs_override) {

@@ -69,6 +69,10 @@ public:
     // Returns a dtfft error code / DTFFTB_ERROR_*.
     int create(int ndims, const int32_t* dims, int kernel_type, int64_t base_storage, const int32_t* neighbor_data,
                int n_neighbors, int effort, bool force_effort);
+    // Kernel over explicit boxes (one per peer, empty boxes allowed): used by the plan layer
+    // for the fused NVLink path and the brick reshapes, whose geometry is derived from
+    // global-index intersections rather than from neighbor_data.
+    int create_boxes(Family family, int64_t base_storage, const std::vector<Box>& boxes);
     int execute(const void* in, void* out, cudaStream_t stream, int neighbor, bool sync);
     int execute_all(const void* in, void* out, cudaStream_t stream);
     int set_peer_out(void* const* out_bases, const int64_t* out_displs_override);
@@ -91,7 +95,7 @@ private:
     int launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream);
     int pick_unit(const void* in, const void* out) const;
 
-    bool created_ = false, noop_ = true;
+    bool created_ = false, noop_ = true, custom_ = false;
     int ndims_ = 0, type_ = K_DUMMY, P_ = 0;
     int32_t dims_[3] = {1, 1, 1};
     int64_t es_ = 0;

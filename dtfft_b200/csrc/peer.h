@@ -1,0 +1,79 @@
+// Peer-memory registry and device-side barrier for the NVLink direct-store backend.
+//
+// The reference has no counterpart on the NCCL path (its closest relatives are the
+// NVSHMEM symmetric heap of backend_cufftmp, src/dtfft_backend_cufftmp.F90:39-120, and the
+// MPI RMA windows of src/dtfft_backend_mpi.F90:397-431).  On one NVSwitch box every GPU
+// can store straight into every peer's HBM, so a transposition can be ONE kernel that
+// reads the local pencil and writes each element at its final place in the owning peer.
+//
+// * Buffers are "symmetric": every rank registers its buffers collectively and in the
+//   same order (dtfft_mem_alloc does it automatically), so (slot, byte offset) names the
+//   same logical buffer on every rank.  Handles travel as cudaIpcMemHandle_t through the
+//   host allgather; each peer maps them once.
+// * Ordering between GPUs uses a flags array per rank: a one-block kernel stores the
+//   current epoch into every group member's flags with st.release.sys and spins on its
+//   own flags with ld.acquire.sys.  Two such barriers bracket the remote stores
+//   ("destination is free" / "data has landed").
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "comm.h"
+
+namespace dtfftb {
+
+class PeerRegistry {
+public:
+    ~PeerRegistry() { destroy(); }
+    // Collective over `world`.  After it, available() tells whether every rank sits on
+    // the same host with peer access to every other rank's device.
+    int init(const Comm& world);
+    bool available() const { return available_; }
+    const char* why_unavailable() const { return why_; }
+
+    // Collective, same order on every rank.  `ptr` may point inside a larger cudaMalloc
+    // allocation (e.g. a torch caching-allocator segment).
+    int register_buffer(void* ptr, size_t bytes, int* slot_out = nullptr);
+    int unregister_buffer(void* ptr);  // collective
+    bool resolve(const void* ptr, size_t bytes, int* slot, size_t* offset) const;
+    // Address of (slot, offset) of world rank `r` in THIS process' address space.
+    void* peer_ptr(int r, int slot, size_t offset) const;
+
+    // Enqueue a barrier among `members` (world ranks, must contain me) on `stream`.
+    // `channel` separates independent groups (1-D communicator id 1..3, x2 phases).
+    int barrier(const std::vector<int>& members, int channel, cudaStream_t stream);
+    // Non-zero if a barrier ever timed out (peer missing); sticky.
+    int error_state();
+    void destroy();
+
+    static constexpr int kChannels = 10;
+
+private:
+    struct Slot {
+        void* local = nullptr;
+        size_t bytes = 0;
+        std::vector<void*> mapped;  // per world rank (mine = local)
+        std::vector<void*> opened;  // IPC bases to close, per world rank
+        bool live = false;
+    };
+    struct Group {
+        uint64_t** d_peer_flags = nullptr;  // [n] device array: flags base of each member
+        int* d_members = nullptr;           // [n] world ranks
+        int n = 0;
+        uint64_t epoch = 0;
+    };
+    int open_all(const void* base, size_t offset, Slot& s);
+
+    Comm world_;
+    bool inited_ = false, available_ = false;
+    const char* why_ = "not initialised";
+    std::vector<Slot> slots_;
+    uint64_t* flags_ = nullptr;  // [kChannels][world] + error word
+    int flags_slot_ = -1;
+    std::map<std::pair<int, std::vector<int>>, Group> groups_;
+};
+
+}  // namespace dtfftb

@@ -1,0 +1,1273 @@
+// Plan object (see plan.h).  Every block cites the reference lines whose behaviour it restates.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "errors.h"
+
+namespace dtfftb {
+
+namespace {
+
+bool valid_r2r_kind(int k) { return k >= 3 && k <= 10; }
+
+void split(int n, int p, int r, int32_t* start, int32_t* count) { local_size(n, p, r, start, count); }
+
+int cufft_error(cufftResult r) { return r == CUFFT_SUCCESS ? 0 : DTFFTB_ERROR_CUDA_BASE - 5000 - (int)r; }
+
+}  // namespace
+
+// ======================================================================================
+// FFT executor (cuFFT)
+// ======================================================================================
+int FftExecutor::create(int fft_rank, bool r2c, int precision, const Pencil* real, const Pencil& cpx,
+                        cudaStream_t stream) {
+    // abstract_executor%create, src/dtfft_abstract_executor.F90:115-216
+    destroy();
+    r2c_ = r2c;
+    int n[2], inembed[2], onembed[2];
+    long long idist, odist, how_many;
+    const Pencil& base = r2c ? *real : cpx;
+    if (fft_rank == 1) {
+        n[0] = base.counts[0];
+        inembed[0] = n[0];
+        onembed[0] = cpx.counts[0];
+    } else {
+        n[0] = base.counts[1], n[1] = base.counts[0];
+        inembed[0] = n[0], inembed[1] = n[1];
+        onembed[0] = cpx.counts[1], onembed[1] = cpx.counts[0];
+    }
+    idist = 1, odist = 1;
+    for (int i = 0; i < fft_rank; ++i) idist *= inembed[i], odist *= onembed[i];
+    if (idist == 0 || base.size() == 0) return DTFFT_SUCCESS;  // rank without data: no FFT needed
+    how_many = base.size() / idist;
+    if (how_many == 0) return DTFFT_SUCCESS;
+    cufftResult cr;
+    if (!r2c) {  // dtfft_executor_cufft_m.F90:70-79
+        cr = cufftPlanMany(&fwd_, fft_rank, n, inembed, 1, (int)idist, onembed, 1, (int)odist,
+                           precision == DTFFT_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+        bwd_ = fwd_;
+        shared_ = true;
+    } else {  // :80-93
+        cr = cufftPlanMany(&fwd_, fft_rank, n, inembed, 1, (int)idist, onembed, 1, (int)odist,
+                           precision == DTFFT_SINGLE ? CUFFT_R2C : CUFFT_D2Z, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+        cr = cufftPlanMany(&bwd_, fft_rank, n, onembed, 1, (int)odist, inembed, 1, (int)idist,
+                           precision == DTFFT_SINGLE ? CUFFT_C2R : CUFFT_Z2D, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+        shared_ = false;
+    }
+    cr = cufftSetStream(fwd_, stream);
+    if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+    if (!shared_) {
+        cr = cufftSetStream(bwd_, stream);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+    }
+    created_ = true;
+    return DTFFT_SUCCESS;
+}
+
+int FftExecutor::execute(void* a, void* b, int sign) {
+    if (!created_) return DTFFT_SUCCESS;
+    cufftResult cr = cufftXtExec(sign < 0 || shared_ ? fwd_ : bwd_, a, b, sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE);
+    return cufft_error(cr);
+}
+
+void FftExecutor::destroy() {
+    if (created_) {
+        cufftDestroy(fwd_);
+        if (!shared_) cufftDestroy(bwd_);
+    }
+    created_ = false;
+    fwd_ = bwd_ = 0;
+}
+
+// ======================================================================================
+// Plan: creation
+// ======================================================================================
+void Plan::log(const char* fmt, ...) const {
+    if (!cfg_.enable_log || comm_.rank() != 0) return;
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stdout, "dtFFT[b200]: ");
+    vfprintf(stdout, fmt, ap);
+    fprintf(stdout, "\n");
+    fflush(stdout);
+    va_end(ap);
+}
+
+int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_pencil_t* pencil, const int* r2r_kinds,
+                 const dtfftb_comm_t* comm, int precision, int effort, int executor, bool dry) {
+    if (created_) return DTFFT_ERROR_PLAN_IS_CREATED;
+    dry_ = dry;
+    // ---- check_create_args, src/dtfft_plan.F90:2107-2219 ----
+    cfg_ = effective_config();
+    if (cfg_.platform != DTFFT_PLATFORM_CUDA) return DTFFT_ERROR_INVALID_PLATFORM;
+    kind_ = kind;
+    comm_ = Comm(comm);
+    if (dims) {
+        if (ndims != 2 && ndims != 3) return DTFFT_ERROR_INVALID_N_DIMENSIONS;
+        for (int i = 0; i < ndims; ++i)
+            if (dims[i] <= 0) return DTFFT_ERROR_INVALID_DIMENSION_SIZE;
+        ndims_ = ndims;
+        for (int i = 0; i < 3; ++i) user_dims_[i] = i < ndims ? dims[i] : 1;
+    } else {
+        if (!pencil || pencil->ndims == 0) return DTFFT_ERROR_PENCIL_NOT_INITIALIZED;
+        ndims_ = pencil->ndims;
+    }
+    if (precision != DTFFT_SINGLE && precision != DTFFT_DOUBLE) return DTFFT_ERROR_INVALID_PRECISION;
+    if (effort < DTFFT_ESTIMATE || effort > DTFFT_EXHAUSTIVE) return DTFFT_ERROR_INVALID_EFFORT;
+    if (executor < DTFFT_EXECUTOR_NONE || executor > DTFFT_EXECUTOR_VKFFT) return DTFFT_ERROR_INVALID_EXECUTOR;
+    if (executor != DTFFT_EXECUTOR_NONE && executor != DTFFT_EXECUTOR_CUFFT) return DTFFT_ERROR_INVALID_PLATFORM_EXECUTOR;
+    precision_ = precision, effort_ = effort, executor_ = executor;
+    is_transpose_plan_ = executor == DTFFT_EXECUTOR_NONE;
+    if (kind == PLAN_R2R) {
+        if (!is_transpose_plan_) {
+            if (!r2r_kinds) return DTFFT_ERROR_MISSING_R2R_KINDS;
+            for (int i = 0; i < ndims_; ++i)
+                if (!valid_r2r_kind(r2r_kinds[i])) return DTFFT_ERROR_INVALID_R2R_KINDS;
+            return DTFFT_ERROR_R2R_FFT_NOT_SUPPORTED;  // cuFFT has no r2r (dtfft_executor_cufft_m.F90:94-98)
+        }
+        if (r2r_kinds)
+            for (int i = 0; i < ndims_; ++i) r2r_kinds_[i] = r2r_kinds[i];
+    }
+    if (kind == PLAN_R2C && is_transpose_plan_) return DTFFT_ERROR_R2C_TRANSPOSE_PLAN;
+    // storage sizes, src/dtfft_parameters.F90:301-308
+    if (kind == PLAN_R2R)
+        base_storage_ = precision == DTFFT_SINGLE ? 4 : 8;
+    else
+        base_storage_ = precision == DTFFT_SINGLE ? 8 : 16;
+    base_storage_init_ = kind == PLAN_R2C ? base_storage_ / 2 : base_storage_;
+
+    if (dry_) {  // host metadata only (decomposition, sizes, geometry); never executes
+        int rc0 = choose_decomposition(pencil);
+        if (rc0) return rc0;
+        rc0 = build_pencils();
+        if (rc0) return rc0;
+        int wanted0 = cfg_.backend == BACKEND_NONE ? BACKEND_NCCL : cfg_.backend;
+        backend_ = comm_.size() == 1 ? BACKEND_NONE : wanted0;
+        reshape_backend_ = backend_;
+        if (is_final_reshape_enabled_ && is_z_slab_) is_final_reshape_enabled_ = false;
+        created_ = true;
+        return DTFFT_SUCCESS;
+    }
+    // ---- device sanity (src/dtfft_plan.F90:1982-2009): one GPU per rank of this host ----
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        return DTFFT_ERROR_GPU_NOT_SET;
+    }
+    if (cfg_.stream) {
+        stream_ = static_cast<cudaStream_t>(cfg_.stream);
+        own_stream_ = false;
+    } else {  // get_conf_stream, src/dtfft_config.F90:841-852
+        ce = cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        own_stream_ = true;
+    }
+
+    int rc = choose_decomposition(pencil);
+    if (rc) return rc;
+    rc = build_pencils();
+    if (rc) return rc;
+
+    const int P = comm_.size();
+    // ---- backend choice (src/dtfft_config.F90:766-786; transpose_plan.F90:222) ----
+    rc = peers_.init(comm_);
+    if (rc) return rc;
+    int wanted = cfg_.backend == BACKEND_NONE ? BACKEND_NCCL : cfg_.backend;
+    if (wanted != BACKEND_NCCL && wanted != BACKEND_NCCL_PIPELINED && wanted != BACKEND_NVLINK_FUSED)
+        return DTFFT_ERROR_INVALID_BACKEND;
+    if (wanted == BACKEND_NVLINK_FUSED && !peers_.available()) {
+        log("NVLink peer access unavailable (%s): falling back to the NCCL backend", peers_.why_unavailable());
+        wanted = BACKEND_NCCL;
+    }
+    backend_ = P == 1 ? BACKEND_NONE : wanted;
+    if (P > 1) {
+        rc = init_nccl();
+        if (rc) return rc;
+    }
+    if (P > 1 && effort_ >= DTFFT_PATIENT) {  // run_autotune_backend, transpose_plan.F90:634-855
+        rc = autotune_backend();
+        if (rc) return rc;
+    }
+    rc = build_handles(backend_, handles_);
+    if (rc) return rc;
+    reshape_backend_ = backend_;
+    if (cfg_.reshape_backend != BACKEND_NONE && P > 1) {
+        reshape_backend_ = cfg_.reshape_backend;
+        if (reshape_backend_ == BACKEND_NVLINK_FUSED && !peers_.available()) reshape_backend_ = BACKEND_NCCL;
+    }
+    if (is_reshape_enabled_) {
+        rc = build_reshape_handles(reshape_backend_);
+        if (rc) return rc;
+    }
+    if (is_final_reshape_enabled_ && is_z_slab_) is_final_reshape_enabled_ = false;  // dtfft_plan.F90:2093
+    if (!is_transpose_plan_) {
+        rc = create_ffts();
+        if (rc) return rc;
+    }
+    is_aux_alloc_ = false;
+    created_ = true;
+    log("plan created: %dD %s, grid %dx%dx%d, backend %s%s%s", ndims_,
+        kind_ == PLAN_C2C ? "c2c" : kind_ == PLAN_R2C ? "r2c" : "r2r", comm_dims_[0], comm_dims_[1], comm_dims_[2],
+        dtfft_get_backend_string((dtfft_backend_t)backend_), is_z_slab_ ? ", Z-slab" : "", is_y_slab_ ? ", Y-slab" : "");
+    return DTFFT_SUCCESS;
+}
+
+// Process grid, global dims and (for user pencils) every rank's X-aligned box.
+int Plan::choose_decomposition(const dtfft_pencil_t* pencil) {
+    const int P = comm_.size(), me = comm_.rank();
+    const int nd = ndims_;
+    has_user_pencil_ = pencil != nullptr;
+    is_reshape_enabled_ = false;
+    is_final_reshape_enabled_ = false;
+    is_z_slab_ = is_y_slab_ = false;
+    coords_.assign((size_t)P, {0, 0, 0});
+
+    if (!pencil) {
+        for (int i = 0; i < 3; ++i) dims_[i] = user_dims_[i];
+        if (kind_ == PLAN_R2C) dims_[0] = user_dims_[0] / 2 + 1;  // dtfft_plan.F90:2626
+        for (int i = 0; i < 3; ++i) comm_dims_[i] = 1;
+        const dtfftb_comm_t* raw = comm_.raw();
+        if (raw && raw->cart_ndims > 0) {  // user process grid, transpose_plan.F90:128-170
+            const int g = raw->cart_ndims;
+            if (g > nd) return DTFFT_ERROR_INVALID_COMM_DIMS;
+            long long prod = 1;
+            for (int i = 0; i < g; ++i) prod *= raw->cart_dims[i];
+            if (prod != P) return DTFFT_ERROR_INVALID_COMM_DIMS;
+            if (g == nd) {
+                if (raw->cart_dims[0] != 1) return DTFFT_ERROR_INVALID_COMM_FAST_DIM;
+                for (int i = 0; i < nd; ++i) comm_dims_[i] = raw->cart_dims[i];
+            } else if (g == nd - 1) {
+                for (int i = 0; i < g; ++i) comm_dims_[i + 1] = raw->cart_dims[i];
+            } else {
+                comm_dims_[2] = raw->cart_dims[0];
+            }
+            if (nd == 3) {
+                if (comm_dims_[1] == 1 && cfg_.enable_z_slab)
+                    is_z_slab_ = true;
+                else if (comm_dims_[2] == 1 && cfg_.enable_y_slab)
+                    is_y_slab_ = true;
+            }
+        } else {  // transpose_plan.F90:171-203
+            GridChoice g = choose_grid(nd, dims_, P, true, cfg_.enable_z_slab, cfg_.enable_y_slab);
+            for (int i = 0; i < nd; ++i) comm_dims_[i] = g.comm_dims[i];
+            is_z_slab_ = g.is_z_slab, is_y_slab_ = g.is_y_slab;
+            if (g.invalid_grid) log("WARNING: unable to create correct grid decomposition");
+        }
+        for (int r = 0; r < P; ++r) {
+            int32_t c[3] = {0, 0, 0};
+            cart_coords(r, nd, comm_dims_, c);
+            coords_[(size_t)r] = {c[0], c[1], c[2]};
+        }
+        return DTFFT_SUCCESS;
+    }
+
+    // ---- pencil_init%create, src/dtfft_pencil.F90:777-908 ----
+    int err = DTFFT_SUCCESS;
+    if (pencil->ndims < 2 || pencil->ndims > 3) err = DTFFT_ERROR_PENCIL_ARRAYS_INVALID_SIZES;
+    if (!err)
+        for (int i = 0; i < nd; ++i)
+            if (pencil->starts[i] < 0) err = DTFFT_ERROR_PENCIL_INVALID_STARTS;
+    if (!err)
+        for (int i = 0; i < nd; ++i)
+            if (pencil->counts[i] < 0) err = DTFFT_ERROR_PENCIL_INVALID_COUNTS;
+    err = (int)comm_.max((double)err);  // CHECK_ERROR_AND_RETURN_AGG
+    if (err) return err;
+    UserPencil mine{};
+    for (int i = 0; i < 3; ++i) mine.starts[i] = i < nd ? pencil->starts[i] : 0, mine.counts[i] = i < nd ? pencil->counts[i] : 1;
+    if (comm_.allgather_v(mine, user_pencils_)) return DTFFTB_ERROR_COMM;
+    auto& up = user_pencils_;
+    for (int d = 0; d < 3; ++d) user_dims_[d] = 1;
+    for (int d = 0; d < nd; ++d)
+        for (int r = 0; r < P; ++r) user_dims_[d] = std::max(user_dims_[d], up[r].starts[d] + up[r].counts[d]);
+    auto empty = [&](int r) {
+        for (int d = 0; d < nd; ++d)
+            if (up[r].counts[d] == 0) return true;
+        return false;
+    };
+    for (int p1 = 0; p1 < P && !err; ++p1) {  // :838-862 shape mismatch
+        if (empty(p1)) continue;
+        for (int p2 = p1 + 1; p2 < P; ++p2) {
+            if (empty(p2)) continue;
+            for (int d1 = 0; d1 < nd; ++d1)
+                for (int d2 = d1 + 1; d2 < nd; ++d2)
+                    if (up[p1].starts[d1] == up[p2].starts[d1] && up[p1].starts[d2] == up[p2].starts[d2] &&
+                        (up[p1].counts[d1] != up[p2].counts[d1] || up[p1].counts[d2] != up[p2].counts[d2]))
+                        err = DTFFT_ERROR_PENCIL_SHAPE_MISMATCH;
+        }
+    }
+    if (err) return err;
+    for (int i = 0; i < P && !err; ++i)  // :865-873 overlap
+        for (int j = i + 1; j < P; ++j) {
+            if (empty(i) || empty(j)) continue;
+            bool ov = true;
+            for (int d = 0; d < nd; ++d)
+                if (up[i].starts[d] + up[i].counts[d] <= up[j].starts[d] || up[j].starts[d] + up[j].counts[d] <= up[i].starts[d])
+                    ov = false;
+            if (ov) err = DTFFT_ERROR_PENCIL_OVERLAP;
+        }
+    if (err) return err;
+    {  // :875-879 continuity
+        long long vol = 0, gvol = 1;
+        for (int r = 0; r < P; ++r) {
+            if (empty(r)) continue;
+            long long v = 1;
+            for (int d = 0; d < nd; ++d) v *= up[r].counts[d];
+            vol += v;
+        }
+        for (int d = 0; d < nd; ++d) gvol *= user_dims_[d];
+        if (vol != gvol) return DTFFT_ERROR_PENCIL_NOT_CONTINUOUS;
+    }
+    // 1-D communicators of the user's grid (create_1d_comm, :1034-1081): ranks that share
+    // start and extent on every other axis, ordered by their start along the axis
+    int32_t bgrid[3] = {1, 1, 1};
+    std::vector<std::array<int32_t, 3>> bcoord((size_t)P, {0, 0, 0});
+    for (int r = 0; r < P; ++r)
+        for (int d = 0; d < nd; ++d) {
+            std::vector<int32_t> line;
+            for (int i = 0; i < P; ++i) {
+                bool same = true;
+                for (int j = 0; j < nd; ++j)
+                    if (j != d && (up[i].starts[j] != up[r].starts[j] || up[i].counts[j] != up[r].counts[j])) same = false;
+                if (same && (i == r || up[i].starts[d] != up[r].starts[d])) line.push_back(up[i].starts[d]);
+            }
+            std::sort(line.begin(), line.end());
+            int idx = (int)(std::lower_bound(line.begin(), line.end(), up[r].starts[d]) - line.begin());
+            bcoord[(size_t)r][(size_t)d] = idx;
+            if (r == me) bgrid[d] = (int32_t)line.size();
+        }
+    {
+        long long prod = 1;
+        for (int d = 0; d < nd; ++d) prod *= bgrid[d];
+        int bad = prod != P;
+        if (comm_.max(bad) > 0) return DTFFT_ERROR_PENCIL_NOT_CONTINUOUS;
+    }
+    for (int i = 0; i < 3; ++i) dims_[i] = user_dims_[i];
+    if (kind_ == PLAN_R2C) dims_[0] = user_dims_[0] / 2 + 1;
+
+    if (bgrid[0] == 1) {  // X pencils supplied: keep the user's grid (dtfft_plan.F90:2063-2074)
+        for (int d = 0; d < 3; ++d) comm_dims_[d] = d < nd ? bgrid[d] : 1;
+        coords_ = bcoord;
+    } else {
+        // ---- from_bricks, src/dtfft_pencil.F90:520-775 ----
+        is_reshape_enabled_ = true;
+        const int fast = bgrid[0];
+        const int tile = kDefTileSize;
+        int y_size = 1, z_size = 1;
+        bool nice = false;
+        const UserPencil& b0 = up[0];  // rank 0 decides (MPI_Bcast, :640-645)
+        if (nd == 3 && b0.counts[2] > tile * fast) {
+            y_size = 1, z_size = fast, nice = true;
+        } else if (b0.counts[1] > tile * fast || nd == 2) {
+            y_size = fast, z_size = 1, nice = true;
+        } else {
+            for (int i = 2; i <= fast; ++i) {
+                if (fast % i) continue;
+                if (b0.counts[2] < tile * i || b0.counts[2] % i) continue;
+                if (b0.counts[1] < tile * i || b0.counts[1] % i) continue;
+                nice = true;
+                y_size = std::min(i, fast / i), z_size = std::max(i, fast / i);
+                break;
+            }
+        }
+        if (!nice) {
+            int32_t t[2] = {0, 0};
+            dims_create(fast, 2, t);
+            y_size = t[0], z_size = t[1];
+            log("WARNING: unable to find good grid decomposition, using MPI_Dims_create");
+        }
+        comm_dims_[0] = 1, comm_dims_[1] = bgrid[1] * y_size, comm_dims_[2] = nd == 3 ? bgrid[2] * z_size : 1;
+        bricks_.assign((size_t)P, {});
+        xpencil_from_bricks_.assign((size_t)P, UserPencil{});
+        for (int r = 0; r < P; ++r) {
+            const int a = bcoord[(size_t)r][0], b = bcoord[(size_t)r][1], c = nd == 3 ? bcoord[(size_t)r][2] : 0;
+            int ay = 0, az = 0;
+            if (y_size == 1)
+                az = a;
+            else if (z_size == 1)
+                ay = a;
+            else
+                ay = a / z_size, az = a % z_size;
+            coords_[(size_t)r] = {0, b * y_size + ay, c * z_size + az};
+            UserPencil x{};
+            x.starts[0] = 0, x.counts[0] = user_dims_[0];
+            int32_t s, n;
+            split(up[r].counts[1], y_size, ay, &s, &n);
+            x.starts[1] = up[r].starts[1] + s, x.counts[1] = n;
+            if (nd == 3) {
+                split(up[r].counts[2], z_size, az, &s, &n);
+                x.starts[2] = up[r].starts[2] + s, x.counts[2] = n;
+            } else {
+                x.starts[2] = 0, x.counts[2] = 1;
+            }
+            xpencil_from_bricks_[(size_t)r] = x;
+            Pencil bp;
+            bp.aligned_dim = 1, bp.ndims = nd;
+            for (int d = 0; d < nd; ++d) bp.starts[d] = up[r].starts[d], bp.counts[d] = up[r].counts[d];
+            bricks_[(size_t)r][0] = bp;
+        }
+        brick_grid_[0] = bgrid[0], brick_grid_[1] = bgrid[1], brick_grid_[2] = bgrid[2];
+        brick_coords_ = bcoord;
+    }
+    if (nd == 3) {  // transpose_plan.F90:113-125
+        if (comm_dims_[1] == 1 && cfg_.enable_z_slab)
+            is_z_slab_ = true;
+        else if (comm_dims_[2] == 1 && cfg_.enable_y_slab)
+            is_y_slab_ = true;
+    }
+    return DTFFT_SUCCESS;
+}
+
+// X / Y / Z pencils of every rank (create_pencils_and_comm, transpose_plan.F90:1084-1131, with
+// the carry-over rule of pencil%create, src/dtfft_pencil.F90:136-163, for user pencils).
+int Plan::build_pencils() {
+    const int P = comm_.size(), nd = ndims_;
+    pencils_.assign((size_t)P, {});
+    real_pencils_.assign((size_t)P, Pencil{});
+    for (int r = 0; r < P; ++r) {
+        const auto& c = coords_[(size_t)r];
+        Pencil X, Y, Z;
+        X.aligned_dim = 1, Y.aligned_dim = 2, Z.aligned_dim = 3;
+        X.ndims = Y.ndims = Z.ndims = nd;
+        X.starts[0] = 0, X.counts[0] = dims_[0];
+        if (has_user_pencil_) {
+            const UserPencil& u = is_reshape_enabled_ ? xpencil_from_bricks_[(size_t)r] : user_pencils_[(size_t)r];
+            for (int d = 1; d < nd; ++d) X.starts[d] = u.starts[d], X.counts[d] = u.counts[d];
+        } else {
+            for (int d = 1; d < nd; ++d) split(dims_[d], comm_dims_[d], c[(size_t)d], &X.starts[d], &X.counts[d]);
+        }
+        if (nd == 2) {
+            Y.starts[0] = 0, Y.counts[0] = dims_[1];
+            split(dims_[0], comm_dims_[1], c[1], &Y.starts[1], &Y.counts[1]);
+        } else {
+            Y.starts[0] = 0, Y.counts[0] = dims_[1];
+            Y.starts[1] = X.starts[2], Y.counts[1] = X.counts[2];  // z keeps its split
+            split(dims_[0], comm_dims_[1], c[1], &Y.starts[2], &Y.counts[2]);
+            Z.starts[0] = 0, Z.counts[0] = dims_[2];
+            Z.starts[1] = Y.starts[2], Z.counts[1] = Y.counts[2];  // x keeps its split
+            split(dims_[1], comm_dims_[2], c[2], &Z.starts[2], &Z.counts[2]);
+        }
+        pencils_[(size_t)r] = {X, Y, Z};
+        Pencil R = X;  // real-space X pencil of an R2C plan (dtfft_plan.F90:2630)
+        R.counts[0] = user_dims_[0];
+        real_pencils_[(size_t)r] = R;
+    }
+    if (is_reshape_enabled_) {
+        // Z bricks (reshape_plan.F90:150-182): groups of `c` consecutive ranks of the last grid
+        // dimension split z among themselves and pool their share of the slowest axis
+        const int last = nd - 1;
+        const int csize = brick_grid_[last];
+        const int gsize = comm_dims_[last];
+        for (int r = 0; r < P; ++r) {
+            const auto& c = coords_[(size_t)r];
+            const Pencil& L = pencils_[(size_t)r][(size_t)last];  // last pencil: (z,x,y) or (y,x)
+            const int grp = c[(size_t)last] / csize, k = c[(size_t)last] % csize;
+            Pencil B;
+            B.aligned_dim = nd, B.ndims = nd;
+            split(dims_[last], csize, k, &B.starts[0], &B.counts[0]);
+            // pooled slowest axis over the group
+            int lo = 1 << 30, cnt = 0;
+            for (int q = 0; q < P; ++q) {
+                const auto& cq = coords_[(size_t)q];
+                bool same = true;
+                for (int d = 1; d < nd; ++d)
+                    if (d != last && cq[(size_t)d] != c[(size_t)d]) same = false;
+                if (!same || cq[(size_t)last] / csize != grp) continue;
+                const Pencil& Lq = pencils_[(size_t)q][(size_t)last];
+                lo = std::min(lo, (int)Lq.starts[nd - 1]);
+                cnt += Lq.counts[nd - 1];
+            }
+            if (nd == 3) B.starts[1] = L.starts[1], B.counts[1] = L.counts[1];
+            B.starts[nd - 1] = lo, B.counts[nd - 1] = cnt;
+            bricks_[(size_t)r][1] = B;
+        }
+        (void)gsize;
+        is_final_reshape_enabled_ = csize > 1 && cfg_.enable_fourier_reshape;  // reshape_plan.F90:190-191
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::init_nccl() {
+    // backend_helper%create, src/dtfft_abstract_backend.F90:432-457 (MPI_Bcast -> allgather)
+    if (nccl_) return DTFFT_SUCCESS;
+    ncclUniqueId id;
+    std::memset(&id, 0, sizeof(id));
+    if (comm_.rank() == 0) {
+        ncclResult_t nr = ncclGetUniqueId(&id);
+        if (nr != ncclSuccess) return nccl_error(nr);
+    }
+    std::vector<ncclUniqueId> all;
+    if (comm_.allgather_v(id, all)) return DTFFTB_ERROR_COMM;
+    ncclResult_t nr = ncclCommInitRank(&nccl_, comm_.size(), all[0], comm_.rank());
+    if (nr != ncclSuccess) return nccl_error(nr);
+    return DTFFT_SUCCESS;
+}
+
+std::vector<int> Plan::group_members(int rank, int comm_id) const {
+    const int P = comm_.size(), nd = ndims_;
+    std::vector<std::pair<long long, int>> keyed;
+    const auto& c = coords_[(size_t)rank];
+    for (int r = 0; r < P; ++r) {
+        const auto& q = coords_[(size_t)r];
+        if (comm_id == 1) {
+            keyed.push_back({(long long)q[1] * comm_dims_[2] + q[2], r});
+        } else {
+            bool same = true;
+            for (int d = 1; d < nd; ++d)
+                if (d != comm_id - 1 && q[(size_t)d] != c[(size_t)d]) same = false;
+            if (same) keyed.push_back({q[(size_t)(comm_id - 1)], r});
+        }
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<int> out;
+    for (auto& k : keyed) out.push_back(k.second);
+    return out;
+}
+
+int Plan::handle_spec(int type, HandleSpec* hs) const {
+    const int P = comm_.size(), me = comm_.rank(), nd = ndims_;
+    hs->members.clear(), hs->send.clear(), hs->recv.clear();
+    if (std::abs(type) <= 3) {  // transposition: plans(-3:3), transpose_plan.F90:334-361
+        const int at = std::abs(type);
+        if (at < 1 || (nd == 2 && at > 1) || (at == 3 && !is_z_slab_)) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+        hs->ttype = type, hs->rtype = 0;
+        hs->comm_id = transpose_comm_id(type);
+        hs->members = group_members(me, hs->comm_id);
+        int si, ri;
+        transpose_pencil_ids(type, &si, &ri);
+        for (int m : hs->members)
+            hs->send.push_back(pencils_[(size_t)m][(size_t)si]), hs->recv.push_back(pencils_[(size_t)m][(size_t)ri]);
+        hs->es = base_storage_;
+    } else {  // reshape: plans(11:14), reshape_plan.F90:405-438; X reshapes move real elements for R2C
+        if (!is_reshape_enabled_) return DTFFT_ERROR_RESHAPE_NOT_SUPPORTED;
+        if (type < R_X_BRICKS_TO_PENCILS || type > R_Z_BRICKS_TO_PENCILS) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
+        hs->ttype = 0, hs->rtype = type;
+        const bool x_side = type == R_X_BRICKS_TO_PENCILS || type == R_X_PENCILS_TO_BRICKS;
+        const bool to_pencils = type == R_X_BRICKS_TO_PENCILS || type == R_Z_BRICKS_TO_PENCILS;
+        const int last = nd - 1, csize = brick_grid_[last];
+        std::vector<std::pair<int, int>> keyed;
+        for (int r = 0; r < P; ++r) {
+            bool same = true;
+            if (x_side) {  // bricks sharing their (y, z) footprint = one line of the brick grid along x
+                for (int d = 1; d < nd; ++d)
+                    if (brick_coords_[(size_t)r][(size_t)d] != brick_coords_[(size_t)me][(size_t)d]) same = false;
+                if (same) keyed.push_back({brick_coords_[(size_t)r][0], r});
+            } else {  // the `c` consecutive ranks of the last grid dimension that pool their data
+                for (int d = 1; d < nd; ++d)
+                    if (d != last && coords_[(size_t)r][(size_t)d] != coords_[(size_t)me][(size_t)d]) same = false;
+                if (same && coords_[(size_t)r][(size_t)last] / csize == coords_[(size_t)me][(size_t)last] / csize)
+                    keyed.push_back({coords_[(size_t)r][(size_t)last], r});
+            }
+        }
+        std::sort(keyed.begin(), keyed.end());
+        for (auto& k : keyed) hs->members.push_back(k.second);
+        for (int m : hs->members) {
+            const Pencil& brick = bricks_[(size_t)m][x_side ? 0 : 1];
+            const Pencil& pen = x_side ? (kind_ == PLAN_R2C ? real_pencils_[(size_t)m] : pencils_[(size_t)m][0])
+                                       : pencils_[(size_t)m][(size_t)last];
+            hs->send.push_back(to_pencils ? brick : pen);
+            hs->recv.push_back(to_pencils ? pen : brick);
+        }
+        hs->comm_id = x_side ? 4 : 5;  // barrier channels of their own
+        hs->es = x_side ? base_storage_init_ : base_storage_;
+    }
+    hs->me = (int)(std::find(hs->members.begin(), hs->members.end(), me) - hs->members.begin());
+    return DTFFT_SUCCESS;
+}
+
+std::vector<int> Plan::transpose_types() const {
+    std::vector<int> types;
+    for (int d = 1; d < ndims_; ++d) types.push_back(d), types.push_back(-d);
+    if (is_z_slab_) types.push_back(3), types.push_back(-3);
+    return types;
+}
+
+int Plan::build_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& into) {
+    into.clear();
+    HandleContext ctx;
+    ctx.nccl = nccl_;
+    ctx.peers = &peers_;
+    ctx.effort = cfg_.enable_kernel_autotune ? DTFFT_EXHAUSTIVE : effort_;
+    for (int t : transpose_types()) {
+        HandleSpec hs;
+        int rc = handle_spec(t, &hs);
+        if (rc) return rc;
+        std::unique_ptr<ReshapeHandle> h(new ReshapeHandle);
+        int b = hs.members.size() > 1 ? backend : BACKEND_NONE;
+        rc = h->create(ctx, t, 0, hs.comm_id, hs.members, hs.me, hs.send, hs.recv, hs.es, b);
+        if (rc) return rc;
+        into[t] = std::move(h);
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::build_reshape_handles(int backend) {
+    rhandles_.clear();
+    HandleContext ctx;
+    ctx.nccl = nccl_;
+    ctx.peers = &peers_;
+    ctx.effort = effort_;
+    for (int t = R_X_BRICKS_TO_PENCILS; t <= R_Z_BRICKS_TO_PENCILS; ++t) {
+        HandleSpec hs;
+        int rc = handle_spec(t, &hs);
+        if (rc) return rc;
+        std::unique_ptr<ReshapeHandle> h(new ReshapeHandle);
+        int b = hs.members.size() > 1 ? backend : BACKEND_NONE;
+        rc = h->create(ctx, 0, t, hs.comm_id, hs.members, hs.me, hs.send, hs.recv, hs.es, b);
+        if (rc) return rc;
+        rhandles_[t] = std::move(h);
+    }
+    return DTFFT_SUCCESS;
+}
+
+// Introspection for tests / report: the exchange geometry of one transposition or reshape.
+int Plan::describe_exchange(int type, ExchangeDescription* d) const {
+    HandleSpec hs;
+    int rc = handle_spec(type, &hs);
+    if (rc) return rc;
+    const int P = (int)hs.members.size();
+    d->members = hs.members;
+    d->me = hs.me;
+    d->element_bytes = hs.es;
+    d->geo = HandleGeometry{};
+    if (hs.ttype != 0)
+        d->geo = transpose_geometry(hs.ttype, hs.send, hs.recv, hs.me, hs.members, backend_is_pipelined(backend_), false);
+    d->fused.assign((size_t)P, Box{});
+    d->fused_transposing = false;
+    const RankLayout src = layout_of(hs.send[(size_t)hs.me]);
+    for (int i = 0; i < P; ++i) {
+        bool tr = false;
+        d->fused[(size_t)i] = intersect_box(src, layout_of(hs.recv[(size_t)i]), &tr);
+        if (!d->fused[(size_t)i].empty() && tr) d->fused_transposing = true;
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::time_backend(int backend, double* ms) {
+    // execute_autotune, src/dtfft_reshape_plan_base.F90:588-706: every transposition once per
+    // iteration, warm-up + timed iterations, result = max over ranks of the mean
+    std::map<int, std::unique_ptr<ReshapeHandle>> hs;
+    int rc = build_handles(backend, hs);
+    *ms = 1e30;
+    int ok = rc == DTFFT_SUCCESS;
+    if (comm_.sum(ok) != comm_.size()) return DTFFT_SUCCESS;  // backend unusable somewhere: skip it
+    size_t bytes = alloc_bytes(), aux = 0;
+    for (auto& kv : hs) aux = std::max(aux, (size_t)kv.second->aux_bytes());
+    const int saved = backend_;
+    backend_ = backend;  // mem_alloc picks the allocator by backend
+    void *a = nullptr, *b = nullptr, *w = nullptr;
+    rc = mem_alloc(bytes, &a);
+    if (!rc) rc = mem_alloc(bytes, &b);
+    if (!rc && aux) rc = mem_alloc(aux, &w);
+    if (!rc) {
+        cudaMemsetAsync(a, 0, bytes, stream_);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        auto pass = [&]() {
+            int r2 = 0;
+            for (auto& kv : hs) {
+                r2 = kv.second->execute(a, b, stream_, w);
+                if (r2) return r2;
+            }
+            return r2;
+        };
+        for (int i = 0; i < cfg_.n_measure_warmup_iters && !rc; ++i) rc = pass();
+        cudaEventRecord(e0, stream_);
+        for (int i = 0; i < cfg_.n_measure_iters && !rc; ++i) rc = pass();
+        cudaEventRecord(e1, stream_);
+        cudaError_t ce = cudaEventSynchronize(e1);
+        float t = 0;
+        if (!rc && ce == cudaSuccess) {
+            cudaEventElapsedTime(&t, e0, e1);
+            *ms = comm_.max((double)t / std::max(1, (int)cfg_.n_measure_iters));
+        } else {
+            comm_.max(1e30);
+        }
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+    }
+    hs.clear();
+    if (w) mem_free(w);
+    if (b) mem_free(b);
+    if (a) mem_free(a);
+    backend_ = saved;
+    return rc;
+}
+
+int Plan::autotune_backend() {
+    std::vector<int> cands = {BACKEND_NCCL};
+    if (cfg_.enable_pipelined_backends) cands.push_back(BACKEND_NCCL_PIPELINED);
+    if (cfg_.enable_fused_backends && peers_.available()) cands.push_back(BACKEND_NVLINK_FUSED);
+    double best = 1e30;
+    int best_b = backend_;
+    for (int b : cands) {
+        double ms = 1e30;
+        int rc = time_backend(b, &ms);
+        if (rc) return rc;
+        log("autotune backend %s: %.4f ms", dtfft_get_backend_string((dtfft_backend_t)b), ms);
+        if (ms < best) best = ms, best_b = b;
+    }
+    backend_ = best_b;
+    log("DTFFT_PATIENT: selected backend is %s", dtfft_get_backend_string((dtfft_backend_t)backend_));
+    return DTFFT_SUCCESS;
+}
+
+int Plan::create_ffts() {
+    // alloc_fft_plans + create_c2c_core / create_r2c_internal, dtfft_plan.F90:2221-2284, 2543-2556, 2636-2639
+    const int me = comm_.rank(), nd = ndims_;
+    for (int d = 0; d < nd; ++d) fft_mapping_[d] = d;
+    if (!is_z_slab_ && !is_y_slab_) {
+        for (int d = 0; d < nd; ++d)
+            for (int d2 = 0; d2 < d; ++d2) {
+                if (kind_ == PLAN_R2C && (d == 0 || d2 == 0)) continue;
+                const Pencil &a = pencils_[(size_t)me][(size_t)d], &b = pencils_[(size_t)me][(size_t)d2];
+                if (a.counts[0] == b.counts[0] && a.size() == b.size()) {
+                    fft_mapping_[d] = fft_mapping_[d2];
+                    break;
+                }
+            }
+    }
+    const int start = kind_ == PLAN_R2C ? 1 : 0;
+    for (int d = start; d < nd; ++d) {
+        int rank = 1;
+        if ((is_z_slab_ && d == 0) || (is_y_slab_ && d == 1)) rank = 2;
+        if ((is_z_slab_ && d == 1) || (is_y_slab_ && d == 2)) continue;
+        const int m = fft_mapping_[d];
+        if (fft_[m] && fft_[m]->created()) continue;
+        fft_[m].reset(new FftExecutor);
+        int rc = fft_[m]->create(rank, false, precision_, nullptr, pencils_[(size_t)me][(size_t)d], stream_);
+        if (rc) return rc;
+    }
+    if (kind_ == PLAN_R2C) {
+        fft_[0].reset(new FftExecutor);
+        int rc = fft_[0]->create(is_z_slab_ ? 2 : 1, true, precision_, &real_pencils_[(size_t)me], pencils_[(size_t)me][0], stream_);
+        if (rc) return rc;
+    }
+    return DTFFT_SUCCESS;
+}
+
+// ======================================================================================
+// Plan: sizes
+// ======================================================================================
+size_t Plan::element_size() const { return (size_t)(kind_ == PLAN_R2C ? base_storage_ / 2 : base_storage_); }
+
+int Plan::get_local_sizes(int32_t* in_starts, int32_t* in_counts, int32_t* out_starts, int32_t* out_counts,
+                          size_t* alloc) const {
+    // dtfft_plan.F90:1797-1877 + get_local_sizes, src/dtfft_pencil.F90:438-463
+    const int me = comm_.rank(), nd = ndims_;
+    const auto& pz = pencils_[(size_t)me];
+    int out_dim = nd - 1;
+    if (is_y_slab_ && nd == 3) out_dim = 1;
+    auto vol = [&](const Pencil& p) { return (long long)p.size(); };
+    long long internal = 0;
+    for (int d = 0; d < nd; ++d) internal = std::max(internal, vol(pz[(size_t)d]));
+    if (kind_ == PLAN_R2C) internal = std::max(vol(real_pencils_[(size_t)me]), 2 * internal);
+    const Pencil& in_p = kind_ == PLAN_R2C ? real_pencils_[(size_t)me] : pz[0];
+    const Pencil* ip = &in_p;
+    const Pencil* op = &pz[(size_t)out_dim];
+    long long total = internal;
+    if (is_reshape_enabled_) {
+        const Pencil& b1 = bricks_[(size_t)me][0];
+        const Pencil& b2 = bricks_[(size_t)me][1];
+        ip = &b1;
+        long long a1 = vol(b1), a3 = vol(b2);
+        if (kind_ == PLAN_R2C) a3 *= 2;
+        total = std::max(total, std::max(a1, a3));
+        if (is_final_reshape_enabled_) op = &b2;
+    }
+    for (int d = 0; d < nd; ++d) {
+        if (in_starts) in_starts[d] = ip->starts[d];
+        if (in_counts) in_counts[d] = ip->counts[d];
+        if (out_starts) out_starts[d] = op->starts[d];
+        if (out_counts) out_counts[d] = op->counts[d];
+    }
+    if (alloc) *alloc = (size_t)total;
+    return DTFFT_SUCCESS;
+}
+
+size_t Plan::alloc_size() const {
+    size_t a = 0;
+    get_local_sizes(nullptr, nullptr, nullptr, nullptr, &a);
+    return a;
+}
+
+size_t Plan::aux_bytes_transpose() const {
+    size_t a = 0;
+    if (dry_ && backend_is_pipelined(backend_)) {  // abstract_backend.F90:196-201
+        for (int t : transpose_types()) {
+            ExchangeDescription d;
+            if (describe_exchange(t, &d) || d.members.size() < 2) continue;
+            long long s = 0, r = 0;
+            for (auto c : d.geo.send_counts) s += c;
+            for (auto c : d.geo.recv_counts) r += c;
+            a = std::max(a, (size_t)(std::max(s, r) * base_storage_));
+        }
+        return a;
+    }
+    for (auto& kv : handles_) a = std::max(a, (size_t)kv.second->aux_bytes());
+    return a;
+}
+
+size_t Plan::aux_bytes_reshape() const {
+    size_t a = 0;
+    for (auto& kv : rhandles_) a = std::max(a, (size_t)kv.second->aux_bytes());
+    return a;
+}
+
+size_t Plan::aux_bytes() const {  // dtfft_plan.F90:1398-1420
+    return std::max(aux_bytes_transpose(), aux_bytes_reshape()) + alloc_bytes();
+}
+
+int Plan::get_pencil(int layout, dtfft_pencil_t* p) const {
+    // dtfft_plan.F90:1286-1336
+    if (layout < DTFFT_LAYOUT_X_BRICKS || layout > DTFFT_LAYOUT_Z_BRICKS) return DTFFT_ERROR_INVALID_LAYOUT;
+    const int me = comm_.rank();
+    bool valid = true;
+    if (!is_reshape_enabled_ && (layout == DTFFT_LAYOUT_X_BRICKS || layout == DTFFT_LAYOUT_Z_BRICKS)) valid = false;
+    if (ndims_ == 2 && layout == DTFFT_LAYOUT_Z_PENCILS) valid = false;
+    if (layout == DTFFT_LAYOUT_X_PENCILS_FOURIER && kind_ != PLAN_R2C) valid = false;
+    if (!valid) return DTFFT_ERROR_INVALID_LAYOUT;
+    const Pencil* src = nullptr;
+    switch (layout) {
+        case DTFFT_LAYOUT_X_BRICKS: src = &bricks_[(size_t)me][0]; break;
+        case DTFFT_LAYOUT_X_PENCILS: src = kind_ == PLAN_R2C ? &real_pencils_[(size_t)me] : &pencils_[(size_t)me][0]; break;
+        case DTFFT_LAYOUT_X_PENCILS_FOURIER: src = &pencils_[(size_t)me][0]; break;
+        case DTFFT_LAYOUT_Y_PENCILS: src = &pencils_[(size_t)me][1]; break;
+        case DTFFT_LAYOUT_Z_PENCILS: src = &pencils_[(size_t)me][2]; break;
+        default: src = &bricks_[(size_t)me][1]; break;
+    }
+    std::memset(p, 0, sizeof(*p));
+    p->dim = (uint8_t)src->aligned_dim;
+    p->ndims = (uint8_t)ndims_;
+    for (int d = 0; d < ndims_; ++d) p->starts[d] = src->starts[d], p->counts[d] = src->counts[d];
+    p->size = (size_t)src->size();
+    return DTFFT_SUCCESS;
+}
+
+// ======================================================================================
+// Plan: memory (alloc_mem / free_mem, src/dtfft_reshape_plan_base.F90:393-532)
+// ======================================================================================
+int Plan::mem_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return DTFFT_ERROR_INVALID_USAGE;
+    *ptr = nullptr;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (bytes == 0) return DTFFT_ERROR_INVALID_ALLOC_BYTES;
+    Alloc a{};
+    a.bytes = bytes;
+    const bool fused = backend_ == BACKEND_NVLINK_FUSED || reshape_backend_ == BACKEND_NVLINK_FUSED;
+    const bool use_nccl_alloc = nccl_ && !fused && (backend_ == BACKEND_NCCL || backend_ == BACKEND_NCCL_PIPELINED) &&
+                                getenv("DTFFTB_NO_NCCL_MEM") == nullptr;
+    if (use_nccl_alloc) {
+        if (ncclMemAlloc(&a.ptr, bytes) == ncclSuccess) {
+            a.nccl = true;
+            if (ncclCommRegister(nccl_, a.ptr, bytes, &a.reg) != ncclSuccess) a.reg = nullptr;
+        } else {
+            a.ptr = nullptr;
+        }
+    }
+    if (!a.ptr) {
+        cudaError_t ce = cudaMalloc(&a.ptr, bytes);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            return DTFFT_ERROR_ALLOC_FAILED;
+        }
+    }
+    if (fused && comm_.size() > 1 && peers_.available()) {
+        int slot = -1;
+        int rc = peers_.register_buffer(a.ptr, bytes, &slot);
+        if (rc) return rc;
+        a.peer = slot >= 0;
+    }
+    allocs_.push_back(a);
+    *ptr = a.ptr;
+    return DTFFT_SUCCESS;
+}
+
+int Plan::mem_free(void* ptr) {
+    for (size_t i = 0; i < allocs_.size(); ++i) {
+        if (allocs_[i].ptr != ptr) continue;
+        Alloc a = allocs_[i];
+        allocs_.erase(allocs_.begin() + (long)i);
+        if (a.peer) peers_.unregister_buffer(a.ptr);
+        if (a.nccl) {
+            if (a.reg) ncclCommDeregister(nccl_, a.reg);
+            if (ncclMemFree(a.ptr) != ncclSuccess) return DTFFT_ERROR_FREE_FAILED;
+        } else if (cudaFree(a.ptr) != cudaSuccess) {
+            cudaGetLastError();
+            return DTFFT_ERROR_FREE_FAILED;
+        }
+        return DTFFT_SUCCESS;
+    }
+    return DTFFT_ERROR_FREE_FAILED;
+}
+
+int Plan::register_buffer(void* ptr, size_t bytes) {
+    if (!peers_.available() || comm_.size() == 1) return DTFFT_SUCCESS;
+    int slot = -1;
+    int rc = peers_.register_buffer(ptr, bytes, &slot);
+    if (rc) return rc;
+    return slot >= 0 ? DTFFT_SUCCESS : DTFFTB_ERROR_NOT_REGISTERED;
+}
+
+int Plan::unregister_buffer(void* ptr) { return peers_.unregister_buffer(ptr); }
+
+int Plan::check_aux(void* aux, bool from_execute, void** aux1, void** aux2) {
+    // dtfft_plan.F90:2286-2331
+    const size_t shift = alloc_bytes();
+    const bool need2 = aux_bytes_transpose() > 0 || aux_bytes_reshape() > 0;
+    *aux2 = nullptr;
+    if (!is_aux_alloc_ && !aux) {
+        int rc = mem_alloc(aux_bytes(), &aux_ptr_);
+        if (rc) return rc;
+        is_aux_alloc_ = true;
+    }
+    *aux1 = is_aux_alloc_ ? aux_ptr_ : aux;
+    if (from_execute && need2) *aux2 = static_cast<char*>(*aux1) + shift;
+    return DTFFT_SUCCESS;
+}
+
+int Plan::check_device_ptrs(const void* a, const void* b, const void* c) const {
+    // check_device_pointers, dtfft_plan.F90:1769-1795 (is_device_ptr, src/dtfft_helpers.c:9-16)
+    const void* ps[3] = {a, b, c};
+    for (const void* p : ps) {
+        if (!p) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return DTFFT_ERROR_NOT_DEVICE_PTR;
+        }
+        if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return DTFFT_ERROR_NOT_DEVICE_PTR;
+    }
+    return DTFFT_SUCCESS;
+}
+
+// ======================================================================================
+// Plan: execution
+// ======================================================================================
+int Plan::run_transpose(int ttype, void* in, void* out, void* aux) {
+    auto it = handles_.find(ttype);
+    if (it == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+    ReshapeHandle& h = *it->second;
+    stat_launches_ += h.kernel_launches();
+    stat_local_ += h.local_elements() * base_storage_;
+    stat_remote_ += h.remote_elements() * base_storage_;
+    return h.execute(in, out, stream_, aux);
+}
+
+int Plan::run_reshape(int rtype, void* in, void* out, void* aux) {
+    auto it = rhandles_.find(rtype);
+    if (it == rhandles_.end()) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
+    ReshapeHandle& h = *it->second;
+    const int64_t es = (rtype == R_X_BRICKS_TO_PENCILS || rtype == R_X_PENCILS_TO_BRICKS) ? base_storage_init_ : base_storage_;
+    stat_launches_ += h.kernel_launches();
+    stat_local_ += h.local_elements() * es;
+    stat_remote_ += h.remote_elements() * es;
+    return h.execute(in, out, stream_, aux);
+}
+
+int Plan::run_fft(int dim, void* a, void* b, int sign) {
+    FftExecutor* f = fft_[fft_mapping_[dim]].get();
+    if (!f) return DTFFT_SUCCESS;
+    return f->execute(a, b, sign);
+}
+
+int Plan::transpose(void* in, void* out, int ttype, void* aux) {
+    // transpose_private, dtfft_plan.F90:695-747
+    if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    const int at = std::abs(ttype);
+    if (at < 1 || at > 3 || (ndims_ == 2 && at > 1) || (at == 3 && !is_z_slab_)) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+    if (in == out) return DTFFT_ERROR_INPLACE_TRANSPOSE;
+    if (in == aux || out == aux) return DTFFT_ERROR_INVALID_AUX;
+    int rc = check_device_ptrs(in, out, aux);
+    if (rc) return rc;
+    stat_launches_ = stat_local_ = stat_remote_ = 0;
+    void *a1 = nullptr, *a2 = nullptr;
+    if (aux_bytes_transpose() > 0 || aux) {
+        rc = check_aux(aux, false, &a1, &a2);
+        if (rc) return rc;
+    }
+    return run_transpose(ttype, in, out, a1);
+}
+
+int Plan::reshape(void* in, void* out, int rtype, void* aux) {
+    // reshape_private, dtfft_plan.F90:489-544
+    if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (!is_reshape_enabled_) return DTFFT_ERROR_RESHAPE_NOT_SUPPORTED;
+    if (rtype < R_X_BRICKS_TO_PENCILS || rtype > R_Z_BRICKS_TO_PENCILS) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
+    if (in == out) return DTFFT_ERROR_INPLACE_RESHAPE;
+    if (in == aux || out == aux) return DTFFT_ERROR_INVALID_AUX;
+    int rc = check_device_ptrs(in, out, aux);
+    if (rc) return rc;
+    stat_launches_ = stat_local_ = stat_remote_ = 0;
+    void *a1 = nullptr, *a2 = nullptr;
+    if (aux_bytes_reshape() > 0 || aux) {
+        rc = check_aux(aux, false, &a1, &a2);
+        if (rc) return rc;
+    }
+    return run_reshape(rtype, in, out, a1);
+}
+
+int Plan::execute(void* in, void* out, int execute_type, void* aux) {
+    // execute_ptr, dtfft_plan.F90:771-837
+    if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (execute_type != DTFFT_EXECUTE_FORWARD && execute_type != DTFFT_EXECUTE_BACKWARD) return DTFFT_ERROR_INVALID_EXECUTE_TYPE;
+    const bool inplace = in == out;
+    if (is_transpose_plan_ && inplace &&
+        (ndims_ == 2 || is_y_slab_ || (is_reshape_enabled_ && !is_final_reshape_enabled_)))
+        return DTFFT_ERROR_INPLACE_TRANSPOSE;
+    if (in == aux || out == aux) return DTFFT_ERROR_INVALID_AUX;
+    if (is_transpose_plan_ && kind_ == PLAN_R2C) return DTFFT_ERROR_R2C_EXECUTE_CALLED;
+    int rc = check_device_ptrs(in, out, aux);
+    if (rc) return rc;
+    stat_launches_ = stat_local_ = stat_remote_ = 0;
+    void *a1 = nullptr, *a2 = nullptr;
+    rc = check_aux(aux, true, &a1, &a2);
+    if (rc) return rc;
+    const bool fwd = execute_type == DTFFT_EXECUTE_FORWARD;
+    // execute_private, :839-875
+    if (ndims_ == 2 || is_y_slab_)
+        return is_reshape_enabled_ ? execute_2d_reshape(in, out, fwd, a1, a2) : execute_2d(in, out, fwd, a1, a2);
+    if (is_z_slab_)
+        return is_reshape_enabled_ ? execute_z_slab_reshape(in, out, fwd, a1, a2) : execute_z_slab(in, out, fwd, a1, inplace, a2);
+    return is_reshape_enabled_ ? execute_generic_reshape(in, out, fwd, a1, a2) : execute_generic(in, out, fwd, a1, a2);
+}
+
+#define RUN(x)            \
+    do {                  \
+        int rc_ = (x);    \
+        if (rc_) return rc_; \
+    } while (0)
+
+int Plan::execute_2d(void* in, void* out, bool fwd, void* aux, void* aux2) {  // :877-913
+    const int last = 1;  // fft(fft_mapping(2))
+    if (is_transpose_plan_) return run_transpose(fwd ? T_X_TO_Y : T_Y_TO_X, in, out, aux);
+    if (fwd) {
+        RUN(run_fft(0, in, aux, -1));
+        RUN(run_transpose(T_X_TO_Y, aux, out, aux2));
+        RUN(run_fft(last, out, out, -1));
+    } else {
+        RUN(run_fft(last, in, in, +1));
+        RUN(run_transpose(T_Y_TO_X, in, aux, aux2));
+        RUN(run_fft(0, aux, out, +1));
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::execute_2d_reshape(void* in, void* out, bool fwd, void* aux, void* aux2) {  // :915-972
+    if (is_transpose_plan_) {
+        if (fwd) {
+            RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+            if (is_final_reshape_enabled_) {
+                RUN(run_transpose(T_X_TO_Y, aux, in, aux2));
+                RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, in, out, aux2));
+            } else {
+                RUN(run_transpose(T_X_TO_Y, aux, out, aux2));
+            }
+        } else {
+            if (is_final_reshape_enabled_) {
+                RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, out, aux2));
+                RUN(run_transpose(T_Y_TO_X, out, aux, aux2));
+            } else {
+                RUN(run_transpose(T_Y_TO_X, in, aux, aux2));
+            }
+            RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+        }
+        return DTFFT_SUCCESS;
+    }
+    if (fwd) {
+        RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+        RUN(run_fft(0, aux, out, -1));
+        RUN(run_transpose(T_X_TO_Y, out, aux, aux2));
+        if (is_final_reshape_enabled_) {
+            RUN(run_fft(1, aux, aux, -1));
+            RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, aux, out, aux2));
+        } else {
+            RUN(run_fft(1, aux, out, -1));
+        }
+    } else {
+        if (is_final_reshape_enabled_) {
+            RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, aux, aux2));
+            RUN(run_fft(1, aux, aux, +1));
+        } else {
+            RUN(run_fft(1, in, aux, +1));
+        }
+        RUN(run_transpose(T_Y_TO_X, aux, in, aux2));
+        RUN(run_fft(0, in, aux, +1));
+        RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::execute_z_slab(void* in, void* out, bool fwd, void* aux, bool inplace, void* aux2) {  // :974-1016
+    if (is_transpose_plan_) {
+        if (inplace) return execute_generic(in, out, fwd, aux, aux2);
+        return run_transpose(fwd ? T_X_TO_Z : T_Z_TO_X, in, out, aux);
+    }
+    if (fwd) {
+        RUN(run_fft(0, in, aux, -1));
+        RUN(run_transpose(T_X_TO_Z, aux, out, aux2));
+        RUN(run_fft(2, out, out, -1));
+    } else {
+        RUN(run_fft(2, in, in, +1));
+        RUN(run_transpose(T_Z_TO_X, in, aux, aux2));
+        RUN(run_fft(0, aux, out, +1));
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::execute_z_slab_reshape(void* in, void* out, bool fwd, void* aux, void* aux2) {  // :1018-1055
+    if (is_transpose_plan_) {
+        if (fwd) {
+            RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+            RUN(run_transpose(T_X_TO_Z, aux, out, aux2));
+        } else {
+            RUN(run_transpose(T_Z_TO_X, in, aux, aux2));
+            RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+        }
+        return DTFFT_SUCCESS;
+    }
+    if (fwd) {
+        RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+        RUN(run_fft(0, aux, in, -1));
+        RUN(run_transpose(T_X_TO_Z, in, aux, aux2));
+        RUN(run_fft(2, aux, out, -1));
+    } else {
+        RUN(run_fft(2, in, aux, +1));
+        RUN(run_transpose(T_Z_TO_X, aux, in, aux2));
+        RUN(run_fft(0, in, aux, +1));
+        RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::execute_generic(void* in, void* out, bool fwd, void* aux, void* aux2) {  // :1057-1101
+    if (is_transpose_plan_) {
+        if (fwd) {
+            RUN(run_transpose(T_X_TO_Y, in, aux, aux2));
+            RUN(run_transpose(T_Y_TO_Z, aux, out, aux2));
+        } else {
+            RUN(run_transpose(T_Z_TO_Y, in, aux, aux2));
+            RUN(run_transpose(T_Y_TO_X, aux, out, aux2));
+        }
+        return DTFFT_SUCCESS;
+    }
+    if (fwd) {
+        RUN(run_fft(0, in, aux, -1));
+        RUN(run_transpose(T_X_TO_Y, aux, out, aux2));
+        RUN(run_fft(1, out, out, -1));
+        RUN(run_transpose(T_Y_TO_Z, out, aux, aux2));
+        RUN(run_fft(2, aux, out, -1));
+    } else {
+        RUN(run_fft(2, in, aux, +1));
+        RUN(run_transpose(T_Z_TO_Y, aux, in, aux2));
+        RUN(run_fft(1, in, in, +1));
+        RUN(run_transpose(T_Y_TO_X, in, aux, aux2));
+        RUN(run_fft(0, aux, out, +1));
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::execute_generic_reshape(void* in, void* out, bool fwd, void* aux, void* aux2) {  // :1103-1167
+    if (is_transpose_plan_) {
+        if (fwd) {
+            RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+            RUN(run_transpose(T_X_TO_Y, aux, in, aux2));
+            if (is_final_reshape_enabled_) {
+                RUN(run_transpose(T_Y_TO_Z, in, aux, aux2));
+                RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, aux, out, aux2));
+            } else {
+                RUN(run_transpose(T_Y_TO_Z, in, out, aux2));
+            }
+        } else {
+            if (is_final_reshape_enabled_) {
+                RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, aux, aux2));
+                RUN(run_transpose(T_Z_TO_Y, aux, out, aux2));
+            } else {
+                RUN(run_transpose(T_Z_TO_Y, in, out, aux2));
+            }
+            RUN(run_transpose(T_Y_TO_X, out, aux, aux2));
+            RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+        }
+        return DTFFT_SUCCESS;
+    }
+    if (fwd) {
+        RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
+        RUN(run_fft(0, aux, out, -1));
+        RUN(run_transpose(T_X_TO_Y, out, aux, aux2));
+        RUN(run_fft(1, aux, aux, -1));
+        RUN(run_transpose(T_Y_TO_Z, aux, out, aux2));
+        if (is_final_reshape_enabled_) {
+            RUN(run_fft(2, out, aux, -1));
+            RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, aux, out, aux2));
+        } else {
+            RUN(run_fft(2, out, out, -1));
+        }
+    } else {
+        if (is_final_reshape_enabled_) {
+            RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, aux, aux2));
+            RUN(run_fft(2, aux, in, +1));
+        } else {
+            RUN(run_fft(2, in, in, +1));
+        }
+        RUN(run_transpose(T_Z_TO_Y, in, aux, aux2));
+        RUN(run_fft(1, aux, aux, +1));
+        RUN(run_transpose(T_Y_TO_X, aux, in, aux2));
+        RUN(run_fft(0, in, aux, +1));
+        RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
+    }
+    return DTFFT_SUCCESS;
+}
+#undef RUN
+
+int Plan::report() const {
+    // dtfft_plan.F90:1557-1631
+    if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
+    if (comm_.rank() != 0) return DTFFT_SUCCESS;
+    printf("**dtFFT plan report (dtfft_b200)**\n");
+    printf("  dimensions      : %d (", ndims_);
+    for (int d = 0; d < ndims_; ++d) printf("%s%d", d ? "x" : "", user_dims_[d]);
+    printf(")\n  plan type       : %s\n", kind_ == PLAN_C2C ? "C2C" : kind_ == PLAN_R2C ? "R2C" : "R2R");
+    printf("  precision       : %s\n", dtfft_get_precision_string((dtfft_precision_t)precision_));
+    printf("  executor        : %s\n", dtfft_get_executor_string((dtfft_executor_t)executor_));
+    printf("  platform        : CUDA (sm_100a kernels)\n");
+    printf("  process grid    : %dx%dx%d%s%s\n", comm_dims_[0], comm_dims_[1], comm_dims_[2], is_z_slab_ ? " (Z-slab)" : "",
+           is_y_slab_ ? " (Y-slab)" : "");
+    printf("  backend         : %s\n", dtfft_get_backend_string((dtfft_backend_t)backend_));
+    if (is_reshape_enabled_) printf("  reshape backend : %s\n", dtfft_get_backend_string((dtfft_backend_t)reshape_backend_));
+    printf("  alloc bytes     : %zu, aux bytes: %zu\n", alloc_bytes(), aux_bytes());
+    fflush(stdout);
+    return DTFFT_SUCCESS;
+}
+
+int Plan::destroy() {
+    // dtfft_plan.F90:1169-1250
+    if (stream_) cudaStreamSynchronize(stream_);
+    handles_.clear();
+    rhandles_.clear();
+    for (auto& f : fft_) f.reset();
+    if (is_aux_alloc_ && aux_ptr_) mem_free(aux_ptr_);
+    aux_ptr_ = nullptr;
+    is_aux_alloc_ = false;
+    while (!allocs_.empty()) mem_free(allocs_.back().ptr);
+    peers_.destroy();
+    if (nccl_) ncclCommDestroy(nccl_);
+    nccl_ = nullptr;
+    if (own_stream_ && stream_) cudaStreamDestroy(stream_);
+    stream_ = nullptr;
+    own_stream_ = false;
+    created_ = false;
+    cudaGetLastError();
+    return DTFFT_SUCCESS;
+}
+
+}  // namespace dtfftb

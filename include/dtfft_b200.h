@@ -25,6 +25,27 @@ extern "C" {
 #define DTFFTB_ERROR_CUDA_BASE (-10000)
 #define DTFFTB_ERROR_NCCL_BASE (-20000)
 #define DTFFTB_ERROR_INTERNAL (-30000) /* invariant violated (reference: INTERNAL_ERROR) */
+#define DTFFTB_ERROR_NOT_REGISTERED (-30001) /* NVLINK_FUSED backend: `out` is not a registered (dtfft_mem_alloc) buffer */
+#define DTFFTB_ERROR_COMM (-30002) /* the host allgather callback failed */
+
+/* ------------------------------------------------------------------------------------
+ * Process group handed to the plan layer instead of an MPI_Comm.  The reference needs its
+ * communicator only for metadata (Allgather of pencil extents, broadcast of the NCCL id,
+ * MPI_Allreduce of timings: src/dtfft_reshape_handle_generic.F90:143-144,
+ * src/dtfft_abstract_backend.F90:437-441, src/dtfft_reshape_plan_base.F90:588-706); all of
+ * that is expressed with one collective.  `allgather` must copy `bytes` bytes from `send`
+ * of every rank into `recv` (size * bytes, rank order) and return 0.  `cart_ndims` > 0
+ * describes a user process grid (the MPI_Cart_create case of
+ * src/dtfft_transpose_plan.F90:128-170), row-major rank order like MPI.
+ * ---------------------------------------------------------------------------------- */
+typedef struct dtfftb_comm_s {
+    int32_t rank;
+    int32_t size;
+    void* ctx;
+    int (*allgather)(void* ctx, const void* send, void* recv, int64_t bytes);
+    int32_t cart_ndims;
+    int32_t cart_dims[3];
+} dtfftb_comm_t;
 
 /* kernel_type_t values: src/dtfft_abstract_kernel.F90:59-98 */
 enum {

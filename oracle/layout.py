@@ -298,3 +298,123 @@ def plan_geometry(dims, comm_dims, ttype: int, pipelined=False, fused=False):
                                        [pencils[m][ri] for m in members], me, members,
                                        pipelined=pipelined, fused=fused))
     return pencils, geos
+
+
+# --------------------------------------------------------------------------------------
+# User pencils and bricks (plans created from dtfft_pencil_t)
+# --------------------------------------------------------------------------------------
+def grid_from_boxes(starts, counts):
+    """Per-axis 1-D communicators of a user decomposition (``create_1d_comm``,
+    src/dtfft_pencil.F90:1034-1081): for every rank r and axis d, the ranks that share start and
+    extent on every OTHER axis, ordered by their start along d.  Returns ``(grid, coords)``:
+    ``grid[d]`` = communicator size along d (taken from rank 0; the reference aborts unless the
+    product equals the world size, :889-899), ``coords[r][d]`` = r's rank in that communicator."""
+    P, nd = len(starts), len(starts[0])
+    coords = [[0] * nd for _ in range(P)]
+    grid = [1] * nd
+    for r in range(P):
+        for d in range(nd):
+            line = sorted(starts[i][d] for i in range(P)
+                          if all(starts[i][j] == starts[r][j] and counts[i][j] == counts[r][j]
+                                 for j in range(nd) if j != d)
+                          and (i == r or starts[i][d] != starts[r][d]))
+            coords[r][d] = line.index(starts[r][d])
+            if r == 0:
+                grid[d] = len(line)
+    return grid, coords
+
+
+def pencils_from_x(dims, comm_dims, coords, x_starts, x_counts):
+    """X / Y / Z pencils when the X pencil is prescribed (user pencil or from_bricks):
+    ``create_pencils_and_comm`` with ``ipencil`` (src/dtfft_transpose_plan.F90:1113-1122) +
+    the carry-over rule of ``pencil%create`` (src/dtfft_pencil.F90:136-163): the axis that stays
+    distributed between consecutive pencils keeps its split, the newly distributed axis gets the
+    standard ``get_local_size`` split."""
+    nd = len(dims)
+    X = Pencil(1, list(x_starts), list(x_counts))
+    if nd == 2:
+        s, c = local_size(dims[0], comm_dims[1], coords[1])
+        return [X, Pencil(2, [0, s], [dims[1], c])]
+    s, c = local_size(dims[0], comm_dims[1], coords[1])
+    Y = Pencil(2, [0, X.starts[2], s], [dims[1], X.counts[2], c])
+    s2, c2 = local_size(dims[1], comm_dims[2], coords[2])
+    Z = Pencil(3, [0, Y.starts[2], s2], [dims[2], Y.counts[2], c2])
+    return [X, Y, Z]
+
+
+def from_bricks(brick_starts, brick_counts, cuda=True):
+    """``pencil_init%from_bricks`` (src/dtfft_pencil.F90:520-775) for a non-cartesian communicator.
+    Input: every rank's brick (x fastest).  Returns ``(dims, comm_dims, coords, x_starts, x_counts,
+    brick_grid, brick_coords)`` of the X pencils the bricks are reshaped to: the ``P0`` ranks that
+    share a (y, z) footprint split the brick's z (if it is long enough: > tile * P0), else y,
+    else a ``y_size x z_size`` factorisation (:607-655); new grid = ``1 x P1*y_size x P2*z_size``."""
+    P, nd = len(brick_starts), len(brick_starts[0])
+    dims = [max(brick_starts[r][d] + brick_counts[r][d] for r in range(P)) for d in range(nd)]
+    bgrid, bcoords = grid_from_boxes(brick_starts, brick_counts)
+    fast = bgrid[0]
+    tile = DEF_TILE_SIZE if cuda else 4
+    c0 = brick_counts[0]  # rank 0 decides and broadcasts (:640-645)
+    y_size = z_size = None
+    if nd == 3 and c0[2] > tile * fast:
+        y_size, z_size = 1, fast
+    elif c0[1] > tile * fast or nd == 2:
+        y_size, z_size = fast, 1
+    else:
+        for i in range(2, fast + 1):
+            if fast % i:
+                continue
+            if c0[2] < tile * i or c0[2] % i:
+                continue
+            if c0[1] < tile * i or c0[1] % i:
+                continue
+            y_size, z_size = min(i, fast // i), max(i, fast // i)
+            break
+    if y_size is None:
+        y_size, z_size = dims_create(fast, 2, [0, 0])
+    comm_dims = [1, bgrid[1] * y_size, (bgrid[2] * z_size) if nd == 3 else 1][:nd]
+    coords, xs, xc = [], [], []
+    for r in range(P):
+        a, b = bcoords[r][0], bcoords[r][1]
+        c = bcoords[r][2] if nd == 3 else 0
+        if y_size == 1:
+            ay, az = 0, a
+        elif z_size == 1:
+            ay, az = a, 0
+        else:  # MPI_Cart_create(y_size x z_size) over the x-line, row-major (:689-706)
+            ay, az = a // z_size, a % z_size
+        s1, n1 = local_size(brick_counts[r][1], y_size, ay)
+        st, ct = [0, brick_starts[r][1] + s1], [dims[0], n1]
+        co = [0, b * y_size + ay]
+        if nd == 3:
+            s2, n2 = local_size(brick_counts[r][2], z_size, az)
+            st.append(brick_starts[r][2] + s2)
+            ct.append(n2)
+            co.append(c * z_size + az)
+        coords.append(co)
+        xs.append(st)
+        xc.append(ct)
+    return dims, comm_dims, coords, xs, xc, bgrid, bcoords
+
+
+def z_bricks(dims, comm_dims, coords, last_pencils, brick_grid):
+    """``bricks(2)`` of the reshape plan (src/dtfft_reshape_plan.F90:150-182): groups of ``c``
+    consecutive ranks of the last grid dimension (c = brick-grid size along the last axis) split
+    the pencil's aligned axis among themselves and pool their share of the slowest axis.
+    ``last_pencils[r]`` = rank r's last pencil (Z pencil in 3-D, Y pencil in 2-D)."""
+    P, nd = len(coords), len(dims)
+    last = nd - 1
+    csize = brick_grid[last]
+    out = []
+    for r in range(P):
+        grp, k = divmod(coords[r][last], csize)
+        s0, c0 = local_size(dims[last], csize, k)
+        mates = [q for q in range(P) if coords[q][last] // csize == grp
+                 and all(coords[q][d] == coords[r][d] for d in range(1, nd) if d != last)]
+        lo = min(last_pencils[q].starts[nd - 1] for q in mates)
+        cnt = sum(last_pencils[q].counts[nd - 1] for q in mates)
+        L = last_pencils[r]
+        if nd == 3:
+            out.append(Pencil(3, [s0, L.starts[1], lo], [c0, L.counts[1], cnt]))
+        else:
+            out.append(Pencil(2, [s0, lo], [c0, cnt]))
+    return out

@@ -116,3 +116,28 @@ def transpose_generic(inputs, dims, comm_dims, ttype, pipelined=False, fused=Fal
         else:
             execute(g.unpack_kernel, g.recv_dims, a[r], b[r], g.recv_nd)
     return [b[r][: pencils[r][ri].size] for r in range(n)]
+
+
+# --------------------------------------------------------------------------------------
+# Ground truth for ANY exchange (transposition or brick reshape) + emulation of the product's
+# fused-store geometry
+# --------------------------------------------------------------------------------------
+def redistribute(G, pencils_dst):
+    """What the host MPI-datatype path delivers for any redistribution
+    (src/dtfft_reshape_handle_datatype.F90:436-847): every rank ends up with the global array
+    restricted to its destination box, stored in the destination axis order."""
+    return [pencil_slice(G, p) for p in pencils_dst]
+
+
+def apply_boxes(src, dsts, boxes, members):
+    """Emulate the NVLINK_FUSED kernel of one rank on the host: ``boxes[i]`` =
+    (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2) places the part of ``src`` owned by member i
+    straight into ``dsts[members[i]]`` (include/dtfft_b200_api.h: dtfftb_plan_describe_exchange)."""
+    for i, b in enumerate(boxes):
+        n0, n1, n2, ioff, ooff, is1, is2, os0, os1, os2 = (int(v) for v in b)
+        if n0 <= 0 or n1 <= 0 or n2 <= 0:
+            continue
+        a, bb, c = np.meshgrid(np.arange(n0), np.arange(n1), np.arange(n2), indexing="ij")
+        iidx = (ioff + a + bb * is1 + c * is2).ravel()
+        oidx = (ooff + a * os0 + bb * os1 + c * os2).ravel()
+        dsts[members[i]][oidx] = src[iidx]

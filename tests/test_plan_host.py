@@ -1,0 +1,336 @@
+"""Host logic of the plan layer on CPU: decomposition, sizes and exchange geometry computed by
+the C++ library (metadata-only "dry" plans, dtfftb_plan_create_dry) against the oracle, at
+1..8 simulated ranks (tests/fake_comm.py).
+
+Ground truth for every exchange is what the reference's host MPI-datatype path delivers
+(src/dtfft_reshape_handle_datatype.F90:436-847) = slicing a global array; the product's fused
+boxes are replayed in numpy (oracle.pipeline.apply_boxes) and must reproduce it bit for bit.
+"""
+import numpy as np
+import pytest
+
+from dtfft_b200.plan import (Config, DtfftError, Executor, Layout, Pencil, PlanC2C, PlanR2C, PlanR2R, Precision,
+                             Reshape, Transpose)
+from oracle import kernels as K
+from oracle import layout as L
+from oracle import pipeline as P
+from tests.fake_comm import ThreadWorld
+
+LAYOUT_OF_PENCIL = [Layout.X_PENCILS, Layout.Y_PENCILS, Layout.Z_PENCILS]
+
+
+def dry_world(nranks, make_plan, cart_dims=None):
+    """Create one dry plan per simulated rank; returns them (keep alive!)."""
+    if nranks == 1:
+        return [make_plan(0, None)]
+    return ThreadWorld(nranks).run(make_plan, cart_dims)
+
+
+def collect(plans, fn):
+    if len(plans) == 1:
+        return [fn(plans[0])]
+    # describe_exchange etc. are local calls: no collective inside
+    return [fn(p) for p in plans]
+
+
+def pencil_of(plan, layout):
+    p = plan.get_pencil(layout)
+    return L.Pencil(p.dim, p.starts, p.counts)
+
+
+DEFAULT_CASES = [((64, 64, 64), 4), ((512, 512, 512), 8), ((512, 512, 512), 1), ((48, 21, 36), 6), ((13, 7, 9), 6),
+                 ((40, 33, 28), 4), ((129, 99, 33), 3), ((37, 22), 3), ((16384, 16384), 8), ((90, 57), 5),
+                 ((66, 10, 12), 4), ((128, 64, 96), 8), ((1024, 1024, 1024), 8)]
+
+
+@pytest.mark.parametrize("dims,nranks", DEFAULT_CASES)
+@pytest.mark.parametrize("z_slab", [True, False])
+def test_default_decomposition_matches_oracle(dims, nranks, z_slab):
+    """Grid choice, pencils, local sizes (src/dtfft_transpose_plan.F90:170-203, 1084-1131;
+    src/dtfft_pencil.F90:255-279, 438-463)."""
+    cfg = Config(enable_z_slab=z_slab)
+    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True))
+    comm_dims, is_z, is_y = L.choose_grid(list(dims), nranks, cuda=True, z_slab=z_slab, y_slab=False)
+    nd = len(dims)
+    for r, plan in enumerate(plans):
+        assert plan.grid_dims == comm_dims
+        assert plan.z_slab_enabled == is_z and plan.y_slab_enabled == is_y
+        gold = L.make_pencils(list(dims), comm_dims, r)
+        for d in range(nd):
+            got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
+            assert (got.starts, got.counts, got.dim) == (gold[d].starts, gold[d].counts, d + 1)
+        ins, inc, outs, outc, alloc = plan.local_sizes
+        assert (ins, inc) == (gold[0].starts, gold[0].counts)
+        assert (outs, outc) == (gold[nd - 1].starts, gold[nd - 1].counts)
+        assert alloc == max(p.size for p in gold)
+        assert plan.alloc_bytes == alloc * 16 and plan.element_size == 16
+    Config()._commit()
+
+
+@pytest.mark.parametrize("dims,nranks", [c for c in DEFAULT_CASES if np.prod(c[0]) <= 2 ** 21])
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_neighbor_data_matches_oracle(dims, nranks, pipelined):
+    """neighbor_data / counts / displs / kernel kinds of reshape_handle_generic%create
+    (src/dtfft_reshape_handle_generic.F90:291-640) for every transposition of the plan."""
+    cfg = Config(enable_z_slab=True, backend=27 if pipelined else 24)
+    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True))
+    comm_dims, is_z, _ = L.choose_grid(list(dims), nranks)
+    nd = len(dims)
+    ttypes = [1, -1] if nd == 2 else [1, -1, 2, -2] + ([3, -3] if is_z else [])
+    for t in ttypes:
+        _, geos = L.plan_geometry(list(dims), comm_dims, t, pipelined=pipelined)
+        for r, plan in enumerate(plans):
+            d = plan.describe_exchange(t)
+            g = geos[r]
+            assert d["members"] == g.members and d["me"] == g.comm_rank
+            assert d["pack_kernel"] == g.pack_kernel
+            if g.comm_size > 1:
+                assert d["unpack_kernel"] == g.unpack_kernel
+                assert np.array_equal(d["send_nd"], g.send_nd) and np.array_equal(d["recv_nd"], g.recv_nd)
+                assert d["send_counts"].tolist() == g.send_counts and d["send_displs"].tolist() == g.send_displs
+                assert d["recv_counts"].tolist() == g.recv_counts and d["recv_displs"].tolist() == g.recv_displs
+    if pipelined and nranks > 1:
+        # aux = alloc + max(send, recv) bytes of the pipelined backend (dtfft_plan.F90:1398-1420)
+        assert plans[0].aux_bytes > plans[0].alloc_bytes
+    Config()._commit()
+
+
+def replay_fused(plans, type_, src_bufs, dst_sizes, dtype):
+    n = len(plans)
+    dsts = [np.full(dst_sizes[r], -7, dtype) for r in range(n)]
+    for r, plan in enumerate(plans):
+        d = plan.describe_exchange(type_)
+        P.apply_boxes(src_bufs[r], dsts, d["fused_boxes"], d["members"])
+    return dsts
+
+
+@pytest.mark.parametrize("dims,nranks", [c for c in DEFAULT_CASES if np.prod(c[0]) <= 2 ** 19])
+def test_fused_boxes_reproduce_datatype_path(dims, nranks):
+    """One-kernel NVLink path: replaying every rank's boxes must give exactly the destination
+    pencils of the MPI-datatype path, for every transposition, both directions."""
+    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, dry=True))
+    comm_dims = plans[0].grid_dims
+    nd = len(dims)
+    G = P.global_array(dims, np.complex128, kind="index")
+    ttypes = [1, -1] if nd == 2 else [1, -1, 2, -2] + ([3, -3] if plans[0].z_slab_enabled else [])
+    for t in ttypes:
+        src = P.scatter_input(G, list(dims), comm_dims, t)
+        want = P.transpose_datatype(G, list(dims), comm_dims, t)
+        got = replay_fused(plans, t, src, [w.size for w in want], np.complex128)
+        for r in range(nranks):
+            assert np.array_equal(got[r], want[r]), (L.TRANSPOSE_NAMES[t], r)
+
+
+# ---------------------------------------------------------------------------------------------
+# user pencils and bricks
+# ---------------------------------------------------------------------------------------------
+def split_uneven(n, parts):
+    """cut points like the reference's C test (3/4 - 1/4 split, tests/c/test_c2c_3d_c.c:128-136)"""
+    if parts == 1:
+        return [(0, n)]
+    if parts == 2:
+        a = (3 * n) // 4
+        return [(0, a), (a, n - a)]
+    out, s = [], 0
+    for i in range(parts):
+        c = n // parts + (1 if i < n % parts else 0)  # remainder to the FIRST ranks: not dtFFT's own rule
+        out.append((s, c))
+        s += c
+    return out
+
+
+def user_x_pencils(dims, grid):
+    """X pencils (x undistributed) over a py x pz process grid with uneven user cuts."""
+    ys, zs = split_uneven(dims[1], grid[0]), split_uneven(dims[2], grid[1])
+    boxes = []
+    for iz in range(grid[1]):
+        for iy in range(grid[0]):
+            boxes.append(([0, ys[iy][0], zs[iz][0]], [dims[0], ys[iy][1], zs[iz][1]]))
+    return boxes
+
+
+@pytest.mark.parametrize("dims,grid", [((512, 64, 96), (2, 2)), ((20, 13, 17), (3, 2)), ((33, 9, 8), (1, 4)),
+                                       ((16, 12, 40), (4, 1))])
+def test_user_pencils(dims, grid):
+    """Plans created from dtfft_pencil_t keep the user's split (src/dtfft_pencil.F90:136-163,
+    777-908); every transposition still reproduces the datatype path."""
+    boxes = user_x_pencils(dims, grid)
+    n = len(boxes)
+    cfg = Config(enable_z_slab=False)
+    plans = dry_world(n, lambda r, c: PlanC2C(Pencil(*boxes[r]), comm=c, config=cfg, dry=True))
+    starts, counts = [b[0] for b in boxes], [b[1] for b in boxes]
+    ggrid, coords = L.grid_from_boxes(starts, counts)
+    assert ggrid == [1, grid[0], grid[1]]
+    G = P.global_array(dims, np.float64, kind="index")
+    pencils = []
+    for r, plan in enumerate(plans):
+        assert plan.dims == list(dims) and plan.grid_dims == ggrid
+        gold = L.pencils_from_x(list(dims), ggrid, coords[r], starts[r], counts[r])
+        pencils.append(gold)
+        for d in range(3):
+            got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
+            assert (got.starts, got.counts) == (gold[d].starts, gold[d].counts), (r, d)
+    for t in (1, -1, 2, -2):
+        si, ri = L.transpose_pencil_ids(t)
+        src = [P.pencil_slice(G, pencils[r][si]) for r in range(n)]
+        want = P.redistribute(G, [pencils[r][ri] for r in range(n)])
+        got = replay_fused(plans, t, src, [w.size for w in want], np.float64)
+        for r in range(n):
+            assert np.array_equal(got[r], want[r]), (t, r)
+    Config()._commit()
+
+
+def brick_boxes(cuts):
+    """cuts = per axis list of extents; rank order x fastest."""
+    edges = [np.concatenate([[0], np.cumsum(c)]) for c in cuts]
+    boxes = []
+    nd = len(cuts)
+    if nd == 3:
+        for k in range(len(cuts[2])):
+            for j in range(len(cuts[1])):
+                for i in range(len(cuts[0])):
+                    boxes.append(([int(edges[0][i]), int(edges[1][j]), int(edges[2][k])],
+                                  [int(cuts[0][i]), int(cuts[1][j]), int(cuts[2][k])]))
+    else:
+        for j in range(len(cuts[1])):
+            for i in range(len(cuts[0])):
+                boxes.append(([int(edges[0][i]), int(edges[1][j])], [int(cuts[0][i]), int(cuts[1][j])]))
+    return boxes
+
+
+BRICK_CASES = [
+    # BASELINE config 5: 768x512x1024, brick grid 2x2x2, uneven non-power-of-two cuts
+    ([[300, 468], [200, 312], [500, 524]], True),
+    ([[30, 34], [20, 12], [70, 58]], False),          # z long enough at tile 32? no -> y / factorised split
+    ([[10, 6, 8], [9, 11], [12, 8]], False),          # 3 bricks along x
+    ([[10, 6], [40, 24], [5, 7]], False),
+    ([[20, 13, 7], [16, 17]], False),                 # 2-D bricks
+]
+
+
+@pytest.mark.parametrize("cuts,metadata_only", BRICK_CASES)
+def test_bricks_to_pencils(cuts, metadata_only):
+    """from_bricks + the four reshapes (src/dtfft_pencil.F90:520-775, src/dtfft_reshape_plan.F90:
+    150-182): X pencils, Z bricks and the reshape exchanges against the oracle."""
+    boxes = brick_boxes(cuts)
+    n = len(boxes)
+    nd = len(cuts)
+    cfg = Config(enable_fourier_reshape=True, enable_z_slab=False)
+    plans = dry_world(n, lambda r, c: PlanR2R(Pencil(*boxes[r]), comm=c, config=cfg, dry=True))
+    starts, counts = [b[0] for b in boxes], [b[1] for b in boxes]
+    dims, comm_dims, coords, xs, xc, bgrid, _ = L.from_bricks(starts, counts)
+    pencils = [L.pencils_from_x(dims, comm_dims, coords[r], xs[r], xc[r]) for r in range(n)]
+    zb = L.z_bricks(dims, comm_dims, coords, [p[nd - 1] for p in pencils], bgrid)
+    for r, plan in enumerate(plans):
+        assert plan.dims == dims and plan.grid_dims == comm_dims
+        b1 = plan.get_pencil(Layout.X_BRICKS)
+        assert (b1.starts, b1.counts) == (starts[r], counts[r])
+        for d in range(nd):
+            got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
+            assert (got.starts, got.counts) == (pencils[r][d].starts, pencils[r][d].counts), (r, d)
+        b2 = plan.get_pencil(Layout.Z_BRICKS)
+        assert (b2.starts, b2.counts) == (zb[r].starts, zb[r].counts), r
+        ins, inc, outs, outc, alloc = plan.local_sizes
+        assert (ins, inc) == (starts[r], counts[r])
+        assert alloc >= max(int(np.prod(counts[r])), max(p.size for p in pencils[r]), zb[r].size)
+    if nd == 3 and cuts == BRICK_CASES[0][0]:
+        # pencil grid 1x2x4, X pencils 768 x {200|312} x {250|250|262|262}
+        assert comm_dims == [1, 2, 4]
+        assert sorted({tuple(p[0].counts) for p in pencils}) == [(768, 200, 250), (768, 200, 262), (768, 312, 250),
+                                                                  (768, 312, 262)]
+        assert {tuple(p[1].counts) for p in pencils} == {(512, 250, 384), (512, 262, 384)}
+        assert {tuple(p[2].counts) for p in pencils} == {(1024, 384, 128)}
+    if metadata_only:
+        Config()._commit()
+        return
+    G = P.global_array(dims, np.float64, kind="index")
+    bricks1 = [L.Pencil(1, starts[r], counts[r]) for r in range(n)]
+    xp = [p[0] for p in pencils]
+    lastp = [p[nd - 1] for p in pencils]
+    for rtype, src_l, dst_l in ((Reshape.X_BRICKS_TO_PENCILS, bricks1, xp), (Reshape.X_PENCILS_TO_BRICKS, xp, bricks1),
+                                (Reshape.Z_PENCILS_TO_BRICKS, lastp, zb), (Reshape.Z_BRICKS_TO_PENCILS, zb, lastp)):
+        src = P.redistribute(G, src_l)
+        want = P.redistribute(G, dst_l)
+        got = replay_fused(plans, rtype, src, [w.size for w in want], np.float64)
+        for r in range(n):
+            assert np.array_equal(got[r], want[r]), (rtype, r)
+    Config()._commit()
+
+
+# ---------------------------------------------------------------------------------------------
+# R2C sizes, BASELINE configs, validation
+# ---------------------------------------------------------------------------------------------
+def test_r2c_sizes_config3():
+    """BASELINE config 3: 1024^3 R2C fp32, 8 ranks (1x4x2): complex side 513x1024x1024
+    (dtfft_plan.F90:1350-1355, 1868-1876, 2626-2630)."""
+    cfg = Config(enable_z_slab=False)
+    mk = lambda r, c: PlanR2C([1024, 1024, 1024], comm=c, precision=Precision.SINGLE, executor=Executor.CUFFT,
+                              config=cfg, dry=True)
+    # without a user grid the reference keeps the slab-shaped grid 1x1x8 even with the Z-slab
+    # optimisation off (src/dtfft_transpose_plan.F90:193-195); the pencil grid needs a cart comm
+    assert dry_world(8, mk)[0].grid_dims == [1, 1, 8]
+    plans = dry_world(8, mk, cart_dims=[1, 4, 2])
+    p0 = plans[0]
+    assert p0.grid_dims == [1, 4, 2] and p0.element_size == 4
+    ins, inc, outs, outc, alloc = p0.local_sizes
+    assert inc == [1024, 256, 512]
+    assert p0.get_pencil(Layout.X_PENCILS_FOURIER).counts == [513, 256, 512]
+    ycounts = sorted({tuple(p.get_pencil(Layout.Y_PENCILS).counts) for p in plans})
+    assert ycounts == [(1024, 512, 128), (1024, 512, 129)]
+    zcounts = sorted({tuple(p.get_pencil(Layout.Z_PENCILS).counts) for p in plans})
+    assert zcounts == [(1024, 128, 512), (1024, 129, 512)]
+    # alloc in REAL elements = max(real volume, 2 * max complex pencil)
+    for p in plans:
+        cmax = max(int(np.prod(p.get_pencil(l).counts)) for l in (Layout.X_PENCILS_FOURIER, Layout.Y_PENCILS, Layout.Z_PENCILS))
+        assert p.alloc_size == max(1024 * 256 * 512, 2 * cmax)
+    Config()._commit()
+
+
+def test_slab_config4_and_cart_grid():
+    """BASELINE config 4: 16384^2 on 8 ranks = X slabs 16384 x 2048, per-peer block 2048 x 2048;
+    a user process grid (the MPI_Cart_create case) is honoured."""
+    plans = dry_world(8, lambda r, c: PlanC2C([16384, 16384], comm=c, dry=True))
+    assert plans[0].grid_dims == [1, 8]
+    d = plans[3].describe_exchange(Transpose.X_TO_Y)
+    assert d["send_counts"].tolist() == [2048 * 2048] * 8
+    plans = dry_world(8, lambda r, c: PlanC2C([64, 48, 40], comm=c, dry=True), cart_dims=[1, 2, 4])
+    assert plans[0].grid_dims == [1, 2, 4] and not plans[0].z_slab_enabled
+    plans = dry_world(4, lambda r, c: PlanC2C([64, 48, 40], comm=c, dry=True), cart_dims=[4])
+    assert plans[0].grid_dims == [1, 1, 4] and plans[0].z_slab_enabled
+    with pytest.raises(DtfftError) as e:
+        dry_world(4, lambda r, c: PlanC2C([64, 48, 40], comm=c, dry=True), cart_dims=[2, 2, 1])
+    assert e.value.code == 10  # DTFFT_ERROR_INVALID_COMM_FAST_DIM
+
+
+def test_create_argument_validation():
+    """Error codes of check_create_args (src/dtfft_plan.F90:2107-2219) and of the pencil checks
+    (src/dtfft_pencil.F90:777-880; tests/fortran/test_pencils_f.F90:62-222)."""
+    def code(fn):
+        with pytest.raises(DtfftError) as e:
+            fn()
+        return e.value.code
+
+    assert code(lambda: PlanC2C([8], dry=True)) == 3
+    assert code(lambda: PlanC2C([8, 8, 8, 8], dry=True)) == 3
+    assert code(lambda: PlanC2C([8, 0, 8], dry=True)) == 4
+    assert code(lambda: PlanC2C([8, 8, 8], precision=7, dry=True)) == 6
+    assert code(lambda: PlanC2C([8, 8, 8], executor=9, dry=True)) == 8
+    assert code(lambda: PlanC2C([8, 8, 8], executor=Executor.FFTW3, dry=True)) == 401
+    assert code(lambda: PlanR2C([8, 8, 8], dry=True)) == 13           # R2C transpose-only plan
+    assert code(lambda: PlanR2R([8, 8, 8], executor=Executor.CUFFT, dry=True)) == 11  # missing kinds
+    assert code(lambda: PlanC2C(Pencil([0, -1, 0], [4, 4, 4]), dry=True)) == 28
+    assert code(lambda: PlanC2C(Pencil([0, 0, 0], [4, -4, 4]), dry=True)) == 27
+    # overlapping / non-tiling user pencils on 2 ranks
+    boxes = [([0, 0, 0], [8, 4, 8]), ([0, 3, 0], [8, 5, 8])]
+    assert code(lambda: dry_world(2, lambda r, c: PlanC2C(Pencil(*boxes[r]), comm=c, dry=True))) == 30
+    boxes = [([0, 0, 0], [8, 4, 8]), ([0, 5, 0], [8, 3, 8])]
+    assert code(lambda: dry_world(2, lambda r, c: PlanC2C(Pencil(*boxes[r]), comm=c, dry=True))) == 31
+    # a dry plan never executes
+    p = PlanC2C([8, 8, 8], dry=True)
+    assert code(lambda: p.mem_alloc(64)) == 203
+    # config validation (src/dtfft_config.F90:677-764)
+    assert code(lambda: Config(n_measure_iters=0)._commit()) == 34
+    assert code(lambda: Config(platform=1)._commit()) == 400
+    assert code(lambda: Config(backend=22)._commit()) == 402
+    assert code(lambda: Config(backend=77)._commit()) == 202
+    Config()._commit()
