@@ -157,107 +157,165 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _plan_cycle(plan, Execute, a, b, aux):
+    """One fwd+bwd transpose-only cycle through the public API: X->Y->Z then Z->Y->X (2 calls)."""
+    plan.execute(a, b, Execute.FORWARD, aux)
+    plan.execute(b, a, Execute.BACKWARD, aux)
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from dtfft_b200.kernel import KERNEL_PERMUTE_BACKWARD, KERNEL_PERMUTE_FORWARD, Kernel
+    from dtfft_b200.comm import TorchComm
+    from dtfft_b200.plan import Backend, Config, Execute, PlanC2C, Transpose
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world != 1:
-        raise SystemExit("multi-GPU bench arrives with the plan layer (N=1 only in this revision)")
+        comm = TorchComm()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
     n = N_GLOBAL
     dims = [n, n, n]
-    N = n ** 3
-    stream = torch.cuda.current_stream()
-    a = torch.empty(2 * N, dtype=torch.float64, device="cuda")
-    a.uniform_(0, 1)
-    b = torch.empty_like(a)
-    fwd = Kernel().create(dims, 0, ES, KERNEL_PERMUTE_FORWARD)
-    bwd = Kernel().create(dims, 0, ES, KERNEL_PERMUTE_BACKWARD)
-    info = fwd.info()
+    names = {"nccl": Backend.NCCL, "nccl_pipe": Backend.NCCL_PIPELINED, "nvlink": Backend.NVLINK_FUSED}
+    if world == 1:
+        cand = [("single", Backend.NONE)]
+    elif args.backend == "auto":
+        cand = list(names.items())
+    else:
+        cand = [(args.backend, names[args.backend])]
 
-    def cycle(x, y):  # X->Y->Z->Y->X ; result back in x
-        fwd.execute(x, y, stream)
-        fwd.execute(y, x, stream)
-        bwd.execute(x, y, stream)
-        bwd.execute(y, x, stream)
-
-    ref_sum = float(a.sum())
-    for _ in range(args.warmup):
-        cycle(a, b)
-    torch.cuda.synchronize()
-    assert float(a.sum()) == ref_sum, "cycle is not the identity"
-
-    # ---- device-resident timing ------------------------------------------------------------
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    results = {}
+    best = None
+    for bname, backend in cand:
+        # the plan enqueues on a stream torch owns (dtfft_config_t.stream), so torch's allocators
+        # may record events on it for as long as they like
+        stream = torch.cuda.Stream()
+        cfg = Config(enable_z_slab=False, backend=backend, stream=stream)
+        plan = PlanC2C(dims, comm=comm, config=cfg)
+        assert plan.stream == stream.cuda_stream
+        nbytes = plan.alloc_bytes
+        bufs = [plan.mem_alloc(nbytes) for _ in range(2)]
+        aux_buf = plan.mem_alloc(plan.aux_bytes)
+        a, b = (torch.as_tensor(x, device="cuda").view(torch.float64) for x in bufs)
+        aux = torch.as_tensor(aux_buf, device="cuda")
+        n_local = nbytes // ES
+        a[: 2 * n_local].uniform_(0, 1)
+        ref_sum = float(a[: 2 * n_local].sum())
         torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(args.steps):
-            cycle(a, b)
-        e1.record(stream)
+        barrier()
+        for _ in range(args.warmup):
+            _plan_cycle(plan, Execute, a, b, aux)
+        stream.synchronize()
+        assert float(a[: 2 * n_local].sum()) == ref_sum, "cycle is not the identity"
         torch.cuda.synchronize()
-    total_ms = e0.elapsed_time(e1)
-    ms_per_step = total_ms / args.steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        with ClockSampler(local_rank) as clocks:
+            barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(args.steps):
+                plan.execute(a, b, Execute.FORWARD, aux)
+                launches += plan.stats()["kernel_launches"]
+                plan.execute(b, a, Execute.BACKWARD, aux)
+                launches += plan.stats()["kernel_launches"]
+            e1.record(stream)
+            stream.synchronize()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        results[bname] = {"plan": plan, "ms": ms, "launches": launches, "clocks": clocks.summary(), "a": a, "b": b,
+                          "aux": aux, "stream": stream, "bufs": bufs + [aux_buf], "n_local": n_local,
+                          "backend": plan.backend.name}
+        if best is None or ms < results[best]["ms"]:
+            best = bname
+    R = results[best]
+    plan, a, b, aux, stream, n_local = R["plan"], R["a"], R["b"], R["aux"], R["stream"], R["n_local"]
+    ms_per_step = R["ms"]
     value = CYCLE_BYTES / (ms_per_step * 1e-3) / 1e9
-    launches = 4 * args.steps
 
-    # ---- per-launch timing of the dominant kernel (events around each launch) ---------------
+    # ---- per-transposition timing (events around each dtfft_transpose) -----------------------
+    order = [(Transpose.X_TO_Y, a, b), (Transpose.Y_TO_Z, b, a), (Transpose.Z_TO_Y, a, b), (Transpose.Y_TO_X, b, a)]
     evs = []
     reps = min(args.steps, 10)
+    barrier()
     for _ in range(reps):
-        for k, (x, y) in ((fwd, (a, b)), (fwd, (b, a)), (bwd, (a, b)), (bwd, (b, a))):
-            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record(stream)
-            k.execute(x, y, stream)
-            t.record(stream)
-            evs.append((s, t))
-    torch.cuda.synchronize()
-    kms = [s.elapsed_time(t) for s, t in evs]
-    k_avg_ms = sum(kms) / len(kms)
-    k_bytes = 2 * N * ES
+        for t, x, y in order:
+            s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(stream)
+            plan.transpose(x, y, t, aux)
+            t_.record(stream)
+            evs.append((s_, t_, plan.stats()))
+    stream.synchronize()
+    kms = [s_.elapsed_time(t_) for s_, t_, _ in evs]
+    k_avg_ms = max_over_ranks(sum(kms) / len(kms))
+    per_type = {}
+    for i, (t, _, _) in enumerate(order):
+        per_type[t.name] = max_over_ranks(sum(kms[i::4]) / len(kms[i::4]))
+    k_bytes = 2 * n_local * ES  # one read + one write of the local pencil
     achieved = k_bytes / (k_avg_ms * 1e-3) / 1e9
+    remote = sum(st["remote_bytes"] for _, _, st in evs) / len(evs)
     peak, peak_src = measured_peaks()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
-    if os.path.exists(tpath):
+    if world == 1 and os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("transpose_tiles_kernel_bytes_per_launch")
         except Exception:
             traffic = None
+    if world == 1:
+        kernel_name = "transpose_tiles_kernel<uint4,2,2,8> (one launch per transposition)"
+    elif R["backend"] == "NVLINK_FUSED":
+        kernel_name = "transpose_tiles_kernel<uint4,2,2,8> with peer-mapped destinations (+2 peer_barrier_kernel)"
+    else:
+        kernel_name = "transpose_tiles_kernel (pack) + ncclSend/Recv + rows_copy_kernel (unpack)"
 
     # ---- end to end with host buffers (H2D + cycle + D2H inside the timed region) -----------
-    h_in = torch.empty(2 * N, dtype=torch.float64, pin_memory=True)
-    h_in.copy_(a)
-    h_out = torch.empty(2 * N, dtype=torch.float64, pin_memory=True)
+    h_in = torch.empty(2 * n_local, dtype=torch.float64, pin_memory=True)
+    h_in.copy_(a[: 2 * n_local])
+    h_out = torch.empty(2 * n_local, dtype=torch.float64, pin_memory=True)
     e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1):
-        a.copy_(h_in, non_blocking=True)
-        cycle(a, b)
-        h_out.copy_(a, non_blocking=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def e2e_step():
+        with torch.cuda.stream(stream):
+            a[: 2 * n_local].copy_(h_in, non_blocking=True)
+            _plan_cycle(plan, Execute, a, b, aux)
+            h_out.copy_(a[: 2 * n_local], non_blocking=True)
+
+    e2e_step()
+    stream.synchronize()
+    barrier()
     torch.cuda.synchronize()
     e0.record(stream)
     for _ in range(e2e_steps):
-        a.copy_(h_in, non_blocking=True)
-        cycle(a, b)
-        h_out.copy_(a, non_blocking=True)
+        e2e_step()
     e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    stream.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
     assert torch.equal(h_out, h_in), "e2e cycle is not the identity"
     e2e_val = CYCLE_BYTES / (e2e_ms * 1e-3) / 1e9
 
-    # ---- CPU baseline: oracle port on a bounded sample ------------------------------------
+    # ---- CPU baseline: oracle port on a bounded sample (rank 0, N = 1 only) -------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:
         try:
             cpu_cycle_times(256, 1)
             t256, threads = cpu_cycle_times(256, 3)
@@ -269,24 +327,42 @@ def run_ours(args):
         except Exception as ex:  # the baseline is reported, never a gate
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
+    grid = plan.grid_dims
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128 (opaque 16-byte moves)", "data": "synthetic",
-        "config": {"workload": "3D C2C fp64 512^3 transpose-only pencil cycle X->Y->Z->Y->X on 1 B200 (BASELINE configs[1])",
-                   "global_dims": dims, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
-                   "l2": "working set 2 x 2 GiB per permute >> 126 MB L2 (no flush needed)",
-                   "kernel": info},
+        "config": {"workload": f"3D C2C fp64 512^3 transpose-only pencil cycle X->Y->Z->Y->X on {world} B200 "
+                               "(BASELINE configs[1]) through dtfft_execute FORWARD + BACKWARD",
+                   "global_dims": dims, "grid": grid, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
+                   "backend": R["backend"], "transposition_ms": per_type,
+                   "backends_ms_per_step": {k: v["ms"] for k, v in results.items()},
+                   "l2": f"working set 2 x {n_local * ES / 2**20:.0f} MiB per transposition per GPU >> 126 MB L2 (no flush needed)"
+                   if n_local * ES > 2**28 else
+                   f"working set {3 * n_local * ES / 2**20:.0f} MiB over 3 buffers per GPU cycles through L2 (126 MB); buffers alternate so no transposition re-reads what the previous one wrote from L2 alone"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "transpose_tiles_kernel<uint4,2,2,8>", "bytes_per_launch": k_bytes,
+                     "traffic": traffic, "kernel": kernel_name, "bytes_per_launch": k_bytes,
                      "avg_launch_ms": k_avg_ms, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": N * ES,
-                "d2h_bytes_per_step": N * ES, "steps": e2e_steps},
-        "gpu_launches": launches,
-        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n_local * ES * world,
+                "d2h_bytes_per_step": n_local * ES * world, "steps": e2e_steps},
+        "gpu_launches": R["launches"],
+        "clocks": R["clocks"],
     }
-    print(json.dumps(line), flush=True)
+    if world > 1:
+        line["nvlink"] = {"bytes_out_per_transposition_per_gpu": remote, "achieved": remote / (k_avg_ms * 1e-3) / 1e9,
+                          "peak": 900.0, "unit": "GB/s per direction per GPU",
+                          "frac": remote / (k_avg_ms * 1e-3) / 1e9 / 900.0,
+                          "note": "remote payload / mean transposition time (whole step: barriers + local + remote stores)"}
+    for v in results.values():
+        for x in v["bufs"]:
+            v["plan"].mem_free(x)
+        v["plan"].destroy()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -296,6 +372,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--backend", default="auto", choices=["auto", "nccl", "nccl_pipe", "nvlink"],
+                    help="N>1: exchange backend; auto times all three and reports the fastest")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":

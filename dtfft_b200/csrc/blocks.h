@@ -47,6 +47,7 @@ struct BlockDesc {
     long long is1, is2;   // input strides of axes b, c   (axis a has stride 1)
     long long os0, os1, os2;  // output strides of axes a, b, c (family R: os0 == 1)
     long long item_begin; // first work item of this block in the flattened item space
+    long long shuffle;    // blocks[0] only: > 1 -> CTA i works on item (i * shuffle) mod total (coprime multiplier)
     int n0, n1, n2;       // extents along a, b, c
     int tiles0, tiles1;   // tiles along a and b
     FastDiv div0, div1;   // fast division by tiles0 / tiles1

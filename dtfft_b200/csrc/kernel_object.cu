@@ -486,6 +486,25 @@ int Kernel::rebuild_tables() {
         }
         grid_cap_ = grid_mult ? sm_count_ * 8 * grid_mult : 0x7fffffff;
     }
+    // interleave the peers of an all-peer table whose blocks live in different GPUs
+    bool remote = false;
+    for (void* p : peer_out_) remote |= p != nullptr;
+    if (remote && getenv("DTFFTB_NO_SHUFFLE") == nullptr) {
+        for (int slot = 0; slot < 3; ++slot) {
+            const DeviceTable& t = all_[slot];
+            if (t.nblocks < 2 || t.total_items < 4 || t.total_items >= (1ll << 31)) continue;
+            long long s = (long long)(0.6180339887 * (double)t.total_items);
+            auto gcd = [](long long a, long long b) {
+                while (b) {
+                    long long r = a % b;
+                    a = b, b = r;
+                }
+                return a;
+            };
+            while (s > 1 && gcd(s, t.total_items) != 1) --s;
+            host[(size_t)t.offset].shuffle = s;
+        }
+    }
     if (!host.empty()) {
         cudaError_t ce = cudaMalloc(&d_blocks_, host.size() * sizeof(BlockDesc));
         if (ce != cudaSuccess) return cuda_error(ce);

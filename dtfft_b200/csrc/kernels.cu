@@ -73,7 +73,12 @@ __global__ void __launch_bounds__(32 * ROWS)
 
     const int tx = threadIdx.x, ty = threadIdx.y;
 
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
+    // item space, so remote (NVLink-bound) and local (HBM-bound) tiles overlap instead of running
+    // one peer after the other, and no peer sees the traffic of every rank at once.
+    const long long shuffle = __ldg(&blocks[0].shuffle);
+    for (long long it0 = blockIdx.x; it0 < total_items; it0 += gridDim.x) {
+        const long long item = shuffle > 1 ? (it0 * shuffle) % total_items : it0;
         const int bi = find_block(blocks, nblocks, item);
         const BlockDesc& d = blocks[bi];
         const ItemPos p = decode_item(d, item);
@@ -160,7 +165,12 @@ __global__ void __launch_bounds__(kRowsThreads)
     constexpr int UR = kRowsPerThread;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
 
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+    // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
+    // item space, so remote (NVLink-bound) and local (HBM-bound) tiles overlap instead of running
+    // one peer after the other, and no peer sees the traffic of every rank at once.
+    const long long shuffle = __ldg(&blocks[0].shuffle);
+    for (long long it0 = blockIdx.x; it0 < total_items; it0 += gridDim.x) {
+        const long long item = shuffle > 1 ? (it0 * shuffle) % total_items : it0;
         const int bi = find_block(blocks, nblocks, item);
         const BlockDesc& d = blocks[bi];
         const ItemPos p = decode_item(d, item);
