@@ -177,6 +177,18 @@ int per_neighbor_type(int t) {
     }
 }
 
+// B200 tile table, measured at 512^3 with tools/kbench.py (profiles/r01b_kbench.md); replaces the
+// Volta/Ampere model of nvrtc_block_optimizer.  16-byte elements want the smaller 32x64 tile
+// (33 KB smem, 8 independent 16-B loads per thread, ~5 CTAs/SM): 6.8 TB/s vs 5.4 TB/s for the
+// 64x64 tile whose 66.5 KB / 100 registers cap residency at 2 CTAs/SM.
+TileCfg default_tile(int es) {
+    switch (es) {
+        case 16: return TileCfg{1, 2, 8};
+        case 8: return TileCfg{2, 2, 16};
+        default: return TileCfg{2, 2, 8};
+    }
+}
+
 int pow2_ceil(long long v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -291,9 +303,7 @@ int Kernel::create(int ndims, const int32_t* dims, int kernel_type, int64_t base
 
     // B200 tile table (replaces nvrtc_block_optimizer's Volta/Ampere model).
     if (family_ == FAM_T) {
-        // measured on B200 at 512^3 (profiles/r01_kbench.md): 64x64 tiles, 256 threads win for
-        // 4-, 8- and 16-byte elements (6.2-6.4 TB/s vs 6.5 TB/s for a plain device copy)
-        tile_ = TileCfg{2, 2, 8};
+        tile_ = default_tile((int)es_);
         if (const char* e = getenv("DTFFTB_TILE")) {
             int ka, kb, r;
             if (sscanf(e, "%d,%d,%d", &ka, &kb, &r) == 3 && transpose_cfg_supported((int)es_, TileCfg{ka, kb, r}))
@@ -348,7 +358,7 @@ int Kernel::create_boxes(Family family, int64_t base_storage, const std::vector<
     ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
     if (ce != cudaSuccess) return cuda_error(ce);
     if (family_ == FAM_T) {
-        tile_ = TileCfg{2, 2, 8};
+        tile_ = default_tile((int)es_);
         if (const char* e = getenv("DTFFTB_TILE")) {
             int ka, kb, r;
             if (sscanf(e, "%d,%d,%d", &ka, &kb, &r) == 3 && transpose_cfg_supported((int)es_, TileCfg{ka, kb, r}))
