@@ -32,6 +32,27 @@ def describe_error(code: int) -> str:
     return "dtfft_error_t"
 
 
+def _preload_nccl() -> None:
+    """Load the NCCL that torch ships (site-packages/nvidia/nccl) BEFORE our library, so that the
+    `libnccl.so.2` our .so needs resolves to the very copy torch's own NCCL process group uses.
+    Otherwise the dynamic loader would pick the older system libnccl first and a later
+    `import torch` in the same process fails with an undefined NCCL symbol."""
+    import importlib.util
+    import sys
+
+    if "torch" in sys.modules:
+        return  # torch already mapped its NCCL
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            return
+
+
 def lib() -> C.CDLL:
     """Load (once) and return the shared library; raise if it has not been built."""
     global _lib
@@ -41,6 +62,7 @@ def lib() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C dtfft_b200/csrc`. dtfft_b200 has no CPU fallback.")
+    _preload_nccl()
     L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
     L.dtfftb_version.restype = C.c_char_p

@@ -43,3 +43,16 @@ def test_version_and_no_cpu_fallback():
     # host (numpy) buffers are rejected: the product never computes on the CPU
     with pytest.raises(TypeError):
         Kernel().execute(np.zeros(4), np.zeros(4))
+
+
+def test_library_then_torch_share_one_nccl():
+    """Loading libdtfft_b200.so BEFORE torch must not bind the older system libnccl: the loader
+    preloads the NCCL that torch ships, so a later `import torch` finds its own symbols."""
+    import subprocess
+    import sys
+
+    code = ("import dtfft_b200; dtfft_b200.lib(); import torch; "
+            "n=[l.split()[-1] for l in open('/proc/self/maps') if 'libnccl' in l]; "
+            "assert len(set(n)) == 1, set(n); print('one nccl')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert out.returncode == 0 and "one nccl" in out.stdout, out.stderr[-2000:]
