@@ -157,3 +157,10 @@ int oracle_num_threads(void) {
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py asks for
+ * every host core explicitly (n <= 0: all online processors). */
+void oracle_set_num_threads(int n) {
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+}
