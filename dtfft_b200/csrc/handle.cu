@@ -9,6 +9,7 @@ namespace dtfftb {
 
 void ReshapeHandle::destroy() {
     fused_.clear();
+    fused_chunks_.clear();
     fused_boxes_.clear();
     nccl_.reset();
     pack_.reset();
@@ -35,6 +36,8 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
     const int ndims = send.ndims;
     send_elems_ = send.size();
     recv_elems_ = recv.size();
+    send_ = send;
+    recv_by_member_ = recv_by_member;
     int rc;
 
     // element counts that cross the NVLink fabric (everything not addressed to myself)
@@ -148,19 +151,27 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
     return DTFFT_SUCCESS;
 }
 
-int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
+int ReshapeHandle::peer_bases(void* out, std::vector<void*>* bases) {
     PeerRegistry& peers = *ctx_.peers;
     const int P = (int)members_.size();
     int slot = -1;
     size_t off = 0;
     if (!peers.resolve(out, (size_t)(recv_elems_ * es_), &slot, &off)) return DTFFTB_ERROR_NOT_REGISTERED;
+    bases->resize((size_t)P);
+    for (int i = 0; i < P; ++i) (*bases)[(size_t)i] = i == me_ ? out : peers.peer_ptr(members_[(size_t)i], slot, off);
+    return DTFFT_SUCCESS;
+}
+
+int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
+    PeerRegistry& peers = *ctx_.peers;
     auto it = fused_.find(out);
     if (it == fused_.end()) {
-        std::unique_ptr<Kernel> k(new Kernel);
-        int rc = k->create_boxes(fused_family_, es_, fused_boxes_);
+        std::vector<void*> bases;
+        int rc = peer_bases(out, &bases);
         if (rc) return rc;
-        std::vector<void*> bases((size_t)P);
-        for (int i = 0; i < P; ++i) bases[(size_t)i] = i == me_ ? out : peers.peer_ptr(members_[(size_t)i], slot, off);
+        std::unique_ptr<Kernel> k(new Kernel);
+        rc = k->create_boxes(fused_family_, es_, fused_boxes_);
+        if (rc) return rc;
         rc = k->set_peer_out(bases.data(), nullptr);
         if (rc) return rc;
         if (fused_.size() > 16) fused_.clear();
@@ -172,6 +183,59 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
     rc = it->second->execute_all(in, out, stream);
     if (rc) return rc;
     return peers.barrier(members_, 2 * (comm_id_ - 1) + 1, stream);  // every block has landed
+}
+
+int ReshapeHandle::fused_begin(void* out, cudaStream_t stream) {
+    if (!can_chunk()) return DTFFTB_ERROR_INTERNAL;
+    int slot = -1;
+    size_t off = 0;
+    if (!ctx_.peers->resolve(out, (size_t)(recv_elems_ * es_), &slot, &off)) return DTFFTB_ERROR_NOT_REGISTERED;
+    return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1), stream);
+}
+
+int ReshapeHandle::fused_end(cudaStream_t stream) {
+    return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1) + 1, stream);
+}
+
+int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_ctas, cudaStream_t stream) {
+    if (!can_chunk() || k < 0 || k >= nchunks) return DTFFTB_ERROR_INTERNAL;
+    const int P = (int)members_.size();
+    const int nd = send_.ndims;
+    const long long n = slow_extent();
+    auto key = std::make_pair((const void*)out, nchunks);
+    auto it = fused_chunks_.find(key);
+    if (it == fused_chunks_.end()) {
+        std::vector<void*> bases;
+        int rc = peer_bases(out, &bases);
+        if (rc) return rc;
+        std::vector<std::unique_ptr<Kernel>> ks((size_t)nchunks);
+        for (int c = 0; c < nchunks; ++c) {
+            const long long lo = n * c / nchunks, hi = n * (c + 1) / nchunks;
+            // the chunk as a layout of its own: same axes, the slowest one restricted to [lo, hi)
+            Pencil part = send_;
+            part.starts[nd - 1] += (int32_t)lo;
+            part.counts[nd - 1] = (int32_t)(hi - lo);
+            const RankLayout src = layout_of(part);
+            std::vector<Box> boxes((size_t)P);
+            for (int i = 0; i < P; ++i) {
+                bool tr = false;
+                boxes[(size_t)i] = hi > lo ? intersect_box(src, layout_of(recv_by_member_[(size_t)i]), &tr) : Box{};
+            }
+            ks[(size_t)c].reset(new Kernel);
+            rc = ks[(size_t)c]->create_boxes(fused_family_, es_, boxes);
+            if (rc) return rc;
+            rc = ks[(size_t)c]->set_peer_out(bases.data(), nullptr);
+            if (rc) return rc;
+        }
+        if (fused_chunks_.size() > 16) fused_chunks_.clear();
+        it = fused_chunks_.emplace(key, std::move(ks)).first;
+    }
+    Kernel& kern = *it->second[(size_t)k];
+    kern.set_grid_limit(max_ctas);
+    long long slow_stride = 1;  // elements per index of the slowest axis
+    for (int j = 0; j + 1 < nd; ++j) slow_stride *= send_.counts[j];
+    const long long lo = n * k / nchunks;
+    return kern.execute_all(static_cast<char*>(in) + (size_t)(lo * slow_stride) * (size_t)es_, out, stream);
 }
 
 int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {

@@ -53,6 +53,19 @@ public:
     const HandleGeometry& geometry() const { return geo_; }
     void destroy();
 
+    // ---- stage overlap on the NVLINK_FUSED path (no reference counterpart) ----------------
+    // The source pencil is cut along its SLOWEST axis into `nchunks` ranges; chunk k can be
+    // stored to the peers as soon as the producer (an FFT over the same range) has finished,
+    // on another stream, while the producer works on chunk k+1:
+    //     fused_begin(out, s)                      "every member's `out` is free" barrier
+    //     fused_chunk(in, out, k, nchunks, s2) ... persistent kernel limited to `max_ctas` CTAs
+    //     fused_end(s)                             "all blocks have landed" barrier
+    bool can_chunk() const { return created_ && has_exchange_ && backend_ == BACKEND_NVLINK_FUSED && is_transpose_; }
+    long long slow_extent() const { return send_.ndims > 0 ? send_.counts[send_.ndims - 1] : 1; }
+    int fused_begin(void* out, cudaStream_t stream);
+    int fused_chunk(void* in, void* out, int k, int nchunks, int max_ctas, cudaStream_t stream);
+    int fused_end(cudaStream_t stream);
+
 private:
     int execute_fused(void* in, void* out, cudaStream_t stream);
 
@@ -70,6 +83,11 @@ private:
     std::vector<Box> fused_boxes_;  // per member, out_off relative to the member's `out`
     Family fused_family_ = FAM_NONE;
     std::map<const void*, std::unique_ptr<Kernel>> fused_;  // keyed by my `out` pointer
+    Pencil send_;
+    std::vector<Pencil> recv_by_member_;
+    // chunk kernels keyed by (my `out` pointer, nchunks)
+    std::map<std::pair<const void*, int>, std::vector<std::unique_ptr<Kernel>>> fused_chunks_;
+    int peer_bases(void* out, std::vector<void*>* bases);
 };
 
 }  // namespace dtfftb

@@ -539,11 +539,12 @@ int Kernel::pick_unit(const void* in, const void* out) const {
 int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream) {
     if (t.nblocks == 0 || t.total_items == 0) return DTFFT_SUCCESS;
     cudaError_t ce;
+    const int cap = grid_limit_ > 0 ? std::min(grid_cap_, grid_limit_) : grid_cap_;
     if (family_ == FAM_T) {
-        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, grid_cap_, stream);
+        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);
     } else {
         const int slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
-        ce = launch_rows(unit, tx_slot_[slot], in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, grid_cap_, stream);
+        ce = launch_rows(unit, tx_slot_[slot], in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);
     }
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }

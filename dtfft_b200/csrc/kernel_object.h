@@ -77,6 +77,10 @@ public:
     int execute_all(const void* in, void* out, cudaStream_t stream);
     int set_peer_out(void* const* out_bases, const int64_t* out_displs_override);
     int set_tile(int ka, int kb, int rows);
+    // Run as a persistent kernel of at most `max_ctas` CTAs (0 = no limit).  Used when the launch
+    // shares the GPU with another stream (stage overlap): the NVLink-bound stores need few SMs.
+    void set_grid_limit(int max_ctas) { grid_limit_ = max_ctas; }
+    int sm_count() const { return sm_count_; }
     int autotune(const void* in, void* out, cudaStream_t stream, int n_warmup, int n_iters, float* best_ms);
     void destroy();
 
@@ -109,6 +113,7 @@ private:
     int tx_slot_[3] = {32, 32, 32};
     int unit_geo_ = 4;  // widest unit the geometry allows (family R)
     int grid_cap_ = 148 * 8;
+    int grid_limit_ = 0;
     int sm_count_ = 148;
     // device tables: index 0 -> family T (unit = element) or family R unit 4; 1 -> unit 8; 2 -> unit 16
     BlockDesc* d_blocks_ = nullptr;

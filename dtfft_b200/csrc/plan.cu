@@ -24,67 +24,105 @@ int cufft_error(cufftResult r) { return r == CUFFT_SUCCESS ? 0 : DTFFTB_ERROR_CU
 // ======================================================================================
 // FFT executor (cuFFT)
 // ======================================================================================
+int FftExecutor::make_plans(long long how_many, Handles* h) {
+    cufftResult cr;
+    const bool sp = precision_ == DTFFT_SINGLE;
+    if (!r2c_) {  // dtfft_executor_cufft_m.F90:70-79
+        cr = cufftPlanMany(&h->fwd, rank_, n_, inembed_, 1, (int)idist_, onembed_, 1, (int)odist_,
+                           sp ? CUFFT_C2C : CUFFT_Z2Z, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+        h->bwd = h->fwd;
+    } else {  // :80-93
+        cr = cufftPlanMany(&h->fwd, rank_, n_, inembed_, 1, (int)idist_, onembed_, 1, (int)odist_,
+                           sp ? CUFFT_R2C : CUFFT_D2Z, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+        cr = cufftPlanMany(&h->bwd, rank_, n_, onembed_, 1, (int)odist_, inembed_, 1, (int)idist_,
+                           sp ? CUFFT_C2R : CUFFT_Z2D, (int)how_many);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+    }
+    cr = cufftSetStream(h->fwd, stream_);
+    if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+    if (h->bwd != h->fwd) {
+        cr = cufftSetStream(h->bwd, stream_);
+        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
+    }
+    return DTFFT_SUCCESS;
+}
+
 int FftExecutor::create(int fft_rank, bool r2c, int precision, const Pencil* real, const Pencil& cpx,
                         cudaStream_t stream) {
     // abstract_executor%create, src/dtfft_abstract_executor.F90:115-216
     destroy();
     r2c_ = r2c;
-    int n[2], inembed[2], onembed[2];
-    long long idist, odist, how_many;
+    rank_ = fft_rank;
+    precision_ = precision;
+    stream_ = stream;
     const Pencil& base = r2c ? *real : cpx;
     if (fft_rank == 1) {
-        n[0] = base.counts[0];
-        inembed[0] = n[0];
-        onembed[0] = cpx.counts[0];
+        n_[0] = base.counts[0];
+        inembed_[0] = n_[0];
+        onembed_[0] = cpx.counts[0];
     } else {
-        n[0] = base.counts[1], n[1] = base.counts[0];
-        inembed[0] = n[0], inembed[1] = n[1];
-        onembed[0] = cpx.counts[1], onembed[1] = cpx.counts[0];
+        n_[0] = base.counts[1], n_[1] = base.counts[0];
+        inembed_[0] = n_[0], inembed_[1] = n_[1];
+        onembed_[0] = cpx.counts[1], onembed_[1] = cpx.counts[0];
     }
-    idist = 1, odist = 1;
-    for (int i = 0; i < fft_rank; ++i) idist *= inembed[i], odist *= onembed[i];
-    if (idist == 0 || base.size() == 0) return DTFFT_SUCCESS;  // rank without data: no FFT needed
-    how_many = base.size() / idist;
-    if (how_many == 0) return DTFFT_SUCCESS;
-    cufftResult cr;
-    if (!r2c) {  // dtfft_executor_cufft_m.F90:70-79
-        cr = cufftPlanMany(&fwd_, fft_rank, n, inembed, 1, (int)idist, onembed, 1, (int)odist,
-                           precision == DTFFT_SINGLE ? CUFFT_C2C : CUFFT_Z2Z, (int)how_many);
-        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
-        bwd_ = fwd_;
-        shared_ = true;
-    } else {  // :80-93
-        cr = cufftPlanMany(&fwd_, fft_rank, n, inembed, 1, (int)idist, onembed, 1, (int)odist,
-                           precision == DTFFT_SINGLE ? CUFFT_R2C : CUFFT_D2Z, (int)how_many);
-        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
-        cr = cufftPlanMany(&bwd_, fft_rank, n, onembed, 1, (int)odist, inembed, 1, (int)idist,
-                           precision == DTFFT_SINGLE ? CUFFT_C2R : CUFFT_Z2D, (int)how_many);
-        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
-        shared_ = false;
-    }
-    cr = cufftSetStream(fwd_, stream);
-    if (cr != CUFFT_SUCCESS) return cufft_error(cr);
-    if (!shared_) {
-        cr = cufftSetStream(bwd_, stream);
-        if (cr != CUFFT_SUCCESS) return cufft_error(cr);
-    }
+    idist_ = 1, odist_ = 1;
+    for (int i = 0; i < fft_rank; ++i) idist_ *= inembed_[i], odist_ *= onembed_[i];
+    if (idist_ == 0 || base.size() == 0) return DTFFT_SUCCESS;  // rank without data: no FFT needed
+    how_many_ = base.size() / idist_;
+    if (how_many_ == 0) return DTFFT_SUCCESS;
+    const size_t cb = precision == DTFFT_SINGLE ? 8 : 16;
+    out_bytes_ = cb;
+    in_bytes_ = r2c ? cb / 2 : cb;
+    int rc = make_plans(how_many_, &whole_);
+    if (rc) return rc;
     created_ = true;
     return DTFFT_SUCCESS;
 }
 
 int FftExecutor::execute(void* a, void* b, int sign) {
     if (!created_) return DTFFT_SUCCESS;
-    cufftResult cr = cufftXtExec(sign < 0 || shared_ ? fwd_ : bwd_, a, b, sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE);
+    cufftResult cr = cufftXtExec(sign < 0 ? whole_.fwd : whole_.bwd, a, b, sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE);
+    return cufft_error(cr);
+}
+
+int FftExecutor::prepare_range(long long count) {
+    if (!created_ || count <= 0 || count >= how_many_ || by_batch_.count(count)) return DTFFT_SUCCESS;
+    Handles h;
+    int rc = make_plans(count, &h);
+    if (rc) return rc;
+    by_batch_[count] = h;
+    return DTFFT_SUCCESS;
+}
+
+int FftExecutor::execute_range(void* a, void* b, int sign, long long first, long long count) {
+    if (!created_ || count <= 0) return DTFFT_SUCCESS;
+    if (first < 0 || first + count > how_many_) return DTFFTB_ERROR_INTERNAL;
+    const Handles* h = &whole_;
+    if (count != how_many_) {
+        int rc = prepare_range(count);
+        if (rc) return rc;
+        h = &by_batch_.find(count)->second;
+    }
+    // forward reads the `idist` side and writes the `odist` side; backward the other way round
+    const size_t a_off = (size_t)first * (size_t)(sign < 0 ? idist_ : odist_) * (sign < 0 ? in_bytes_ : out_bytes_);
+    const size_t b_off = (size_t)first * (size_t)(sign < 0 ? odist_ : idist_) * (sign < 0 ? out_bytes_ : in_bytes_);
+    cufftResult cr = cufftXtExec(sign < 0 ? h->fwd : h->bwd, static_cast<char*>(a) + a_off, static_cast<char*>(b) + b_off,
+                                 sign < 0 ? CUFFT_FORWARD : CUFFT_INVERSE);
     return cufft_error(cr);
 }
 
 void FftExecutor::destroy() {
-    if (created_) {
-        cufftDestroy(fwd_);
-        if (!shared_) cufftDestroy(bwd_);
-    }
+    auto drop = [](Handles& h) {
+        if (h.fwd) cufftDestroy(h.fwd);
+        if (h.bwd && h.bwd != h.fwd) cufftDestroy(h.bwd);
+        h = Handles{};
+    };
+    drop(whole_);
+    for (auto& kv : by_batch_) drop(kv.second);
+    by_batch_.clear();
     created_ = false;
-    fwd_ = bwd_ = 0;
 }
 
 // ======================================================================================
@@ -125,6 +163,8 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     if (executor < DTFFT_EXECUTOR_NONE || executor > DTFFT_EXECUTOR_VKFFT) return DTFFT_ERROR_INVALID_EXECUTOR;
     if (executor != DTFFT_EXECUTOR_NONE && executor != DTFFT_EXECUTOR_CUFFT) return DTFFT_ERROR_INVALID_PLATFORM_EXECUTOR;
     precision_ = precision, effort_ = effort, executor_ = executor;
+    if (const char* e = getenv("DTFFTB_OVERLAP_CHUNKS")) overlap_chunks_ = std::max(1, atoi(e));
+    if (const char* e = getenv("DTFFTB_OVERLAP_CTAS")) overlap_ctas_ = std::max(0, atoi(e));
     is_transpose_plan_ = executor == DTFFT_EXECUTOR_NONE;
     if (kind == PLAN_R2R) {
         if (!is_transpose_plan_) {
@@ -978,6 +1018,73 @@ int Plan::run_fft(int dim, void* a, void* b, int sign) {
     return f->execute(a, b, sign);
 }
 
+int Plan::run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void* c, void* aux) {
+    FftExecutor* f = fft_[fft_mapping_[dim]].get();
+    auto it = handles_.find(ttype);
+    if (it == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+    ReshapeHandle& h = *it->second;
+    // Peers store into my `c` while I still transform later chunks: `c` must not be the FFT's
+    // source (`b` never is: a transposition is out of place).  Every rank of the group takes
+    // the same decision except ranks without data, whose barriers still pair up.
+    long long nch = overlap_chunks_;
+    const long long slow = h.slow_extent();
+    bool ok = nch > 1 && f && f->created() && h.can_chunk() && c != a && slow > 1 && f->how_many() % slow == 0;
+    if (ok) nch = std::min(nch, slow);
+    if (!ok || nch <= 1) {
+        int rc = run_fft(dim, a, b, sign);
+        if (rc) return rc;
+        return run_transpose(ttype, b, c, aux);
+    }
+    cudaError_t ce;
+    if (!xfer_stream_) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
+        ce = cudaStreamCreateWithPriority(&xfer_stream_, cudaStreamNonBlocking, hi);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaEventCreateWithFlags(&xfer_done_, cudaEventDisableTiming);
+        if (ce != cudaSuccess) return cuda_error(ce);
+    }
+    while ((long long)chunk_events_.size() < nch) {
+        cudaEvent_t e;
+        ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        chunk_events_.push_back(e);
+    }
+    const long long per_slow = f->how_many() / slow;
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int ctas = overlap_ctas_ > 0 ? overlap_ctas_ : sms;
+    int rc = h.fused_begin(c, stream_);
+    if (rc) return rc;
+    for (long long k = 0; k < nch; ++k) {
+        const long long lo = slow * k / nch, hi = slow * (k + 1) / nch;
+        rc = f->execute_range(a, b, sign, lo * per_slow, (hi - lo) * per_slow);
+        if (rc) return rc;
+        ce = cudaEventRecord(chunk_events_[(size_t)k], stream_);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaStreamWaitEvent(xfer_stream_, chunk_events_[(size_t)k], 0);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        // the last chunk has nothing to hide behind: let it use the whole GPU
+        rc = h.fused_chunk(b, c, (int)k, (int)nch, k + 1 < nch ? ctas : 0, xfer_stream_);
+        if (rc) return rc;
+    }
+    ce = cudaEventRecord(xfer_done_, xfer_stream_);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    ce = cudaStreamWaitEvent(stream_, xfer_done_, 0);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    rc = h.fused_end(stream_);
+    if (rc) return rc;
+    stat_launches_ += 2 + nch;
+    stat_local_ += h.local_elements() * base_storage_;
+    stat_remote_ += h.remote_elements() * base_storage_;
+    stat_overlapped_ += 1;
+    return DTFFT_SUCCESS;
+}
+
 int Plan::transpose(void* in, void* out, int ttype, void* aux) {
     // transpose_private, dtfft_plan.F90:695-747
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
@@ -1029,7 +1136,7 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     if (is_transpose_plan_ && kind_ == PLAN_R2C) return DTFFT_ERROR_R2C_EXECUTE_CALLED;
     int rc = check_device_ptrs(in, out, aux);
     if (rc) return rc;
-    stat_launches_ = stat_local_ = stat_remote_ = 0;
+    stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = 0;
     void *a1 = nullptr, *a2 = nullptr;
     rc = check_aux(aux, true, &a1, &a2);
     if (rc) return rc;
@@ -1052,12 +1159,10 @@ int Plan::execute_2d(void* in, void* out, bool fwd, void* aux, void* aux2) {  //
     const int last = 1;  // fft(fft_mapping(2))
     if (is_transpose_plan_) return run_transpose(fwd ? T_X_TO_Y : T_Y_TO_X, in, out, aux);
     if (fwd) {
-        RUN(run_fft(0, in, aux, -1));
-        RUN(run_transpose(T_X_TO_Y, aux, out, aux2));
+        RUN(run_fft_transpose(0, in, aux, -1, T_X_TO_Y, out, aux2));
         RUN(run_fft(last, out, out, -1));
     } else {
-        RUN(run_fft(last, in, in, +1));
-        RUN(run_transpose(T_Y_TO_X, in, aux, aux2));
+        RUN(run_fft_transpose(last, in, in, +1, T_Y_TO_X, aux, aux2));
         RUN(run_fft(0, aux, out, +1));
     }
     return DTFFT_SUCCESS;
@@ -1086,8 +1191,7 @@ int Plan::execute_2d_reshape(void* in, void* out, bool fwd, void* aux, void* aux
     }
     if (fwd) {
         RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
-        RUN(run_fft(0, aux, out, -1));
-        RUN(run_transpose(T_X_TO_Y, out, aux, aux2));
+        RUN(run_fft_transpose(0, aux, out, -1, T_X_TO_Y, aux, aux2));
         if (is_final_reshape_enabled_) {
             RUN(run_fft(1, aux, aux, -1));
             RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, aux, out, aux2));
@@ -1097,11 +1201,10 @@ int Plan::execute_2d_reshape(void* in, void* out, bool fwd, void* aux, void* aux
     } else {
         if (is_final_reshape_enabled_) {
             RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, aux, aux2));
-            RUN(run_fft(1, aux, aux, +1));
+            RUN(run_fft_transpose(1, aux, aux, +1, T_Y_TO_X, in, aux2));
         } else {
-            RUN(run_fft(1, in, aux, +1));
+            RUN(run_fft_transpose(1, in, aux, +1, T_Y_TO_X, in, aux2));
         }
-        RUN(run_transpose(T_Y_TO_X, aux, in, aux2));
         RUN(run_fft(0, in, aux, +1));
         RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
     }
@@ -1114,12 +1217,10 @@ int Plan::execute_z_slab(void* in, void* out, bool fwd, void* aux, bool inplace,
         return run_transpose(fwd ? T_X_TO_Z : T_Z_TO_X, in, out, aux);
     }
     if (fwd) {
-        RUN(run_fft(0, in, aux, -1));
-        RUN(run_transpose(T_X_TO_Z, aux, out, aux2));
+        RUN(run_fft_transpose(0, in, aux, -1, T_X_TO_Z, out, aux2));
         RUN(run_fft(2, out, out, -1));
     } else {
-        RUN(run_fft(2, in, in, +1));
-        RUN(run_transpose(T_Z_TO_X, in, aux, aux2));
+        RUN(run_fft_transpose(2, in, in, +1, T_Z_TO_X, aux, aux2));
         RUN(run_fft(0, aux, out, +1));
     }
     return DTFFT_SUCCESS;
@@ -1138,12 +1239,10 @@ int Plan::execute_z_slab_reshape(void* in, void* out, bool fwd, void* aux, void*
     }
     if (fwd) {
         RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
-        RUN(run_fft(0, aux, in, -1));
-        RUN(run_transpose(T_X_TO_Z, in, aux, aux2));
+        RUN(run_fft_transpose(0, aux, in, -1, T_X_TO_Z, aux, aux2));
         RUN(run_fft(2, aux, out, -1));
     } else {
-        RUN(run_fft(2, in, aux, +1));
-        RUN(run_transpose(T_Z_TO_X, aux, in, aux2));
+        RUN(run_fft_transpose(2, in, aux, +1, T_Z_TO_X, in, aux2));
         RUN(run_fft(0, in, aux, +1));
         RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
     }
@@ -1162,16 +1261,23 @@ int Plan::execute_generic(void* in, void* out, bool fwd, void* aux, void* aux2) 
         return DTFFT_SUCCESS;
     }
     if (fwd) {
-        RUN(run_fft(0, in, aux, -1));
-        RUN(run_transpose(T_X_TO_Y, aux, out, aux2));
-        RUN(run_fft(1, out, out, -1));
-        RUN(run_transpose(T_Y_TO_Z, out, aux, aux2));
+        RUN(run_fft_transpose(0, in, aux, -1, T_X_TO_Y, out, aux2));
+        RUN(run_fft_transpose(1, out, out, -1, T_Y_TO_Z, aux, aux2));
         RUN(run_fft(2, aux, out, -1));
     } else {
-        RUN(run_fft(2, in, aux, +1));
-        RUN(run_transpose(T_Z_TO_Y, aux, in, aux2));
-        RUN(run_fft(1, in, in, +1));
-        RUN(run_transpose(T_Y_TO_X, in, aux, aux2));
+        auto zy = handles_.find(T_Z_TO_Y);
+        if (overlap_chunks_ > 1 && zy != handles_.end() && zy->second->can_chunk()) {
+            // Stage overlap: the reference's choreography (below) transposes back INTO the buffer the
+            // Z transform reads, which forbids storing chunk k while chunk k+1 is still being
+            // transformed.  `in` is scratch on the backward pass anyway (the reference overwrites it
+            // too), so transform it in place and ping-pong in -> aux -> in instead; results are identical.
+            RUN(run_fft_transpose(2, in, in, +1, T_Z_TO_Y, aux, aux2));
+            RUN(run_fft_transpose(1, aux, aux, +1, T_Y_TO_X, in, aux2));
+            RUN(run_fft(0, in, out, +1));
+            return DTFFT_SUCCESS;
+        }
+        RUN(run_fft_transpose(2, in, aux, +1, T_Z_TO_Y, in, aux2));
+        RUN(run_fft_transpose(1, in, in, +1, T_Y_TO_X, aux, aux2));
         RUN(run_fft(0, aux, out, +1));
     }
     return DTFFT_SUCCESS;
@@ -1202,10 +1308,8 @@ int Plan::execute_generic_reshape(void* in, void* out, bool fwd, void* aux, void
     }
     if (fwd) {
         RUN(run_reshape(R_X_BRICKS_TO_PENCILS, in, aux, aux2));
-        RUN(run_fft(0, aux, out, -1));
-        RUN(run_transpose(T_X_TO_Y, out, aux, aux2));
-        RUN(run_fft(1, aux, aux, -1));
-        RUN(run_transpose(T_Y_TO_Z, aux, out, aux2));
+        RUN(run_fft_transpose(0, aux, out, -1, T_X_TO_Y, aux, aux2));
+        RUN(run_fft_transpose(1, aux, aux, -1, T_Y_TO_Z, out, aux2));
         if (is_final_reshape_enabled_) {
             RUN(run_fft(2, out, aux, -1));
             RUN(run_reshape(R_Z_PENCILS_TO_BRICKS, aux, out, aux2));
@@ -1215,13 +1319,11 @@ int Plan::execute_generic_reshape(void* in, void* out, bool fwd, void* aux, void
     } else {
         if (is_final_reshape_enabled_) {
             RUN(run_reshape(R_Z_BRICKS_TO_PENCILS, in, aux, aux2));
-            RUN(run_fft(2, aux, in, +1));
+            RUN(run_fft_transpose(2, aux, in, +1, T_Z_TO_Y, aux, aux2));
         } else {
-            RUN(run_fft(2, in, in, +1));
+            RUN(run_fft_transpose(2, in, in, +1, T_Z_TO_Y, aux, aux2));
         }
-        RUN(run_transpose(T_Z_TO_Y, in, aux, aux2));
-        RUN(run_fft(1, aux, aux, +1));
-        RUN(run_transpose(T_Y_TO_X, aux, in, aux2));
+        RUN(run_fft_transpose(1, aux, aux, +1, T_Y_TO_X, in, aux2));
         RUN(run_fft(0, in, aux, +1));
         RUN(run_reshape(R_X_PENCILS_TO_BRICKS, aux, out, aux2));
     }
@@ -1252,6 +1354,15 @@ int Plan::report() const {
 int Plan::destroy() {
     // dtfft_plan.F90:1169-1250
     if (stream_) cudaStreamSynchronize(stream_);
+    if (xfer_stream_) {
+        cudaStreamSynchronize(xfer_stream_);
+        cudaStreamDestroy(xfer_stream_);
+        xfer_stream_ = nullptr;
+    }
+    for (cudaEvent_t e : chunk_events_) cudaEventDestroy(e);
+    chunk_events_.clear();
+    if (xfer_done_) cudaEventDestroy(xfer_done_);
+    xfer_done_ = nullptr;
     handles_.clear();
     rhandles_.clear();
     for (auto& f : fft_) f.reset();

@@ -46,12 +46,28 @@ public:
     // fft_rank 1 or 2 along the fastest axis (axes) of `cpx` (and `real` for R2C)
     int create(int fft_rank, bool r2c, int precision, const Pencil* real, const Pencil& cpx, cudaStream_t stream);
     int execute(void* a, void* b, int sign);  // sign -1 forward, +1 backward
+    // Stage overlap (no reference counterpart): a contiguous range of the batch,
+    // [first, first + count) of how_many() transforms.  prepare_range builds the cuFFT plan of a
+    // given count ahead of time (plans are cached by count).
+    long long how_many() const { return how_many_; }
+    int prepare_range(long long count);
+    int execute_range(void* a, void* b, int sign, long long first, long long count);
     bool created() const { return created_; }
     void destroy();
 
 private:
-    cufftHandle fwd_ = 0, bwd_ = 0;
-    bool created_ = false, r2c_ = false, shared_ = false;
+    struct Handles {
+        cufftHandle fwd = 0, bwd = 0;
+    };
+    int make_plans(long long how_many, Handles* h);
+    Handles whole_;
+    std::map<long long, Handles> by_batch_;  // chunk plans keyed by their batch count
+    cudaStream_t stream_ = nullptr;
+    int rank_ = 1, n_[2] = {1, 1}, inembed_[2] = {1, 1}, onembed_[2] = {1, 1};
+    long long idist_ = 1, odist_ = 1, how_many_ = 0;
+    size_t in_bytes_ = 16, out_bytes_ = 16;  // element bytes on the forward input / output side
+    int precision_ = 1;
+    bool created_ = false, r2c_ = false;
 };
 
 class Plan {
@@ -97,6 +113,11 @@ public:
         *launches = stat_launches_, *local_bytes = stat_local_, *remote_bytes = stat_remote_;
     }
     int peer_error() { return peers_.error_state(); }
+    // Stage overlap of the cuFFT executor with the NVLINK_FUSED exchange: number of chunks
+    // (<= 1 disables) and CTAs of the persistent exchange kernel (0 = one per SM).
+    void set_overlap(int nchunks, int ctas) { overlap_chunks_ = nchunks, overlap_ctas_ = ctas; }
+    int overlap_chunks() const { return overlap_chunks_; }
+    int64_t overlapped_stages() const { return stat_overlapped_; }
 
     // Exchange geometry of one transposition (dtfft_transpose_t) or reshape (dtfft_reshape_t) on
     // this rank: the reference's neighbor_data tables (transposes) and the fused-path boxes.
@@ -136,6 +157,9 @@ private:
     int run_transpose(int ttype, void* in, void* out, void* aux);
     int run_reshape(int rtype, void* in, void* out, void* aux);
     int run_fft(int dim, void* a, void* b, int sign);
+    // FFT a -> b followed by the transposition b -> c.  With the NVLINK_FUSED backend the two
+    // are pipelined chunk by chunk over two streams (stage overlap); otherwise run back to back.
+    int run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void* c, void* aux);
     int execute_2d(void* in, void* out, bool fwd, void* aux, void* aux2);
     int execute_z_slab(void* in, void* out, bool fwd, void* aux, bool inplace, void* aux2);
     int execute_generic(void* in, void* out, bool fwd, void* aux, void* aux2);
@@ -188,7 +212,12 @@ private:
     std::vector<Alloc> allocs_;
     void* aux_ptr_ = nullptr;
     bool is_aux_alloc_ = false;
-    int64_t stat_launches_ = 0, stat_local_ = 0, stat_remote_ = 0;
+    int64_t stat_launches_ = 0, stat_local_ = 0, stat_remote_ = 0, stat_overlapped_ = 0;
+    // stage overlap
+    int overlap_chunks_ = 4, overlap_ctas_ = 0;
+    cudaStream_t xfer_stream_ = nullptr;
+    std::vector<cudaEvent_t> chunk_events_;
+    cudaEvent_t xfer_done_ = nullptr;
 };
 
 }  // namespace dtfftb

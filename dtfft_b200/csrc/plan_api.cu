@@ -462,6 +462,17 @@ dtfft_error_t dtfftb_plan_get_stats(dtfft_plan_t plan, int64_t* kernel_launches,
     if (remote_bytes) *remote_bytes = c;
     return DTFFT_SUCCESS;
 }
+dtfft_error_t dtfftb_plan_set_overlap(dtfft_plan_t plan, int nchunks, int exchange_ctas) {
+    PLAN_OR_RETURN(plan);
+    P(plan)->set_overlap(nchunks < 1 ? 1 : nchunks, exchange_ctas < 0 ? 0 : exchange_ctas);
+    return DTFFT_SUCCESS;
+}
+dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages) {
+    PLAN_OR_RETURN(plan);
+    if (!n_stages) return DTFFT_ERROR_INVALID_USAGE;
+    *n_stages = P(plan)->overlapped_stages();
+    return DTFFT_SUCCESS;
+}
 dtfft_error_t dtfftb_plan_create_dry(int kind, int8_t ndims, const int32_t* dims, const dtfft_pencil_t* pencil,
                                      dtfft_comm_t comm, dtfft_precision_t precision, dtfft_executor_t executor,
                                      dtfft_plan_t* plan) {

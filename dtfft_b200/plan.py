@@ -392,6 +392,17 @@ class Plan:
         _check(_lib.lib().dtfftb_plan_get_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "dtfftb_plan_get_stats")
         return {"kernel_launches": a.value, "local_bytes": b.value, "remote_bytes": c.value}
 
+    def set_overlap(self, nchunks: int, exchange_ctas: int = 0):
+        """Stage overlap of cuFFT with the NVLINK_FUSED exchange inside execute (extension, see
+        dtfftb_plan_set_overlap): nchunks <= 1 disables.  Same value on every rank."""
+        _check(_lib.lib().dtfftb_plan_set_overlap(self._h, int(nchunks), int(exchange_ctas)), "dtfftb_plan_set_overlap")
+
+    @property
+    def overlapped_stages(self) -> int:
+        n = C.c_int64(0)
+        _check(_lib.lib().dtfftb_plan_get_overlapped_stages(self._h, C.byref(n)), "dtfftb_plan_get_overlapped_stages")
+        return n.value
+
     def describe_exchange(self, type_) -> dict:
         """Exchange geometry of one transposition / reshape on this rank (dtfftb_plan_describe_exchange)."""
         import numpy as np

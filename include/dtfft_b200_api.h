@@ -297,6 +297,15 @@ dtfft_error_t dtfftb_plan_get_stats(dtfft_plan_t plan, int64_t* kernel_launches,
                                     int64_t* remote_bytes);
 /* 0 if healthy; non-zero if a device barrier of the NVLink backend timed out. */
 int dtfftb_plan_peer_error(dtfft_plan_t plan);
+/* Stage overlap of the cuFFT executor with the NVLINK_FUSED exchange inside dtfft_execute
+ * (extension; the reference serialises FFT and exchange on one stream, src/dtfft_plan.F90:1057-1101):
+ * the FFT before a transposition is cut into `nchunks` ranges of its slowest axis and chunk k is
+ * stored to the peers on a second stream while chunk k+1 is transformed.  nchunks <= 1 disables;
+ * `exchange_ctas` = CTAs of the persistent exchange kernel (0 = one per SM).  Default: 4 chunks
+ * (env DTFFTB_OVERLAP_CHUNKS / DTFFTB_OVERLAP_CTAS).  Must be set identically on every rank. */
+dtfft_error_t dtfftb_plan_set_overlap(dtfft_plan_t plan, int nchunks, int exchange_ctas);
+/* Number of FFT+transposition stages of the last dtfft_execute that ran overlapped. */
+dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages);
 
 /* Host-metadata-only plan: decomposition, pencils, sizes and exchange geometry are computed
  * exactly as for a real plan, but no device is touched; execute / transpose / reshape /

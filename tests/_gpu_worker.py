@@ -49,6 +49,8 @@ def main():
         return t.cpu().numpy().view(dtype)[:n]
 
     backends = [Backend.NCCL, Backend.NCCL_PIPELINED, Backend.NVLINK_FUSED]
+    if os.environ.get("DTFFTB_TEST_BACKENDS"):  # e.g. "NVLINK_FUSED": shorter runs on large boxes
+        backends = [Backend[x] for x in os.environ["DTFFTB_TEST_BACKENDS"].split(",")]
     checked = 0
     for backend in backends:
         for dims, z_slab in (([64, 48, 40], False), ([129, 99, 33], False), ([40, 33, 96], True), ([90, 57], False)):
@@ -86,41 +88,48 @@ def main():
         for cls, dims, prec, rdt, cdt, tol in ((PlanC2C, [64, 48, 40], Precision.DOUBLE, np.complex128, np.complex128, 1e-12),
                                                (PlanR2C, [66, 40, 36], Precision.SINGLE, np.float32, np.complex64, 1e-5),
                                                (PlanC2C, [64, 96], Precision.DOUBLE, np.complex128, np.complex128, 1e-12)):
-            nd = len(dims)
-            cfg = Config(backend=backend, enable_z_slab=False)
-            plan = cls(dims, comm=comm, precision=prec, executor=Executor.CUFFT, config=cfg)
-            G = P.global_array(dims, rdt, kind="random")
-            ins, inc, outs, outc, alloc = plan.local_sizes
-            xin = L.Pencil(1, ins, inc)
-            x = P.pencil_slice(G, xin)
-            rev = tuple(range(nd - 1, -1, -1))
-            if cls is PlanR2C:
-                spec = np.fft.rfftn(G.astype(np.float64).transpose(rev)).transpose(rev)
-            else:
-                spec = np.fft.fftn(G.astype(np.complex128))
-            outp = L.Pencil(nd, outs, outc)
-            want = P.pencil_slice(np.asfortranarray(spec), outp)
-            ab, at = dev_buf(plan, plan.alloc_bytes, x)
-            bb, bt = dev_buf(plan, plan.alloc_bytes)
-            cb, ct = dev_buf(plan, plan.alloc_bytes)
-            dist.barrier()
-            plan.execute(at, bt, Execute.FORWARD)
-            sync(plan)
-            got = host(bt, cdt, want.size).astype(np.complex128)
-            num = np.array([np.linalg.norm(got - want) ** 2, np.linalg.norm(want) ** 2])
-            tt = torch.from_numpy(num).cuda()
-            dist.all_reduce(tt)
-            rel = float(torch.sqrt(tt[0] / tt[1]))
-            assert rel <= tol, (backend.name, cls.__name__, rel)
-            plan.execute(bt, ct, Execute.BACKWARD)
-            sync(plan)
-            back = host(ct, rdt, x.size).astype(np.complex128) / np.prod(dims)
-            eps = np.finfo(np.float64 if prec == Precision.DOUBLE else np.float32).eps
-            assert np.max(np.abs(back - x)) <= 5 * np.log2(float(np.prod(dims))) * 2 * eps
-            for b_ in (ab, bb, cb):
-                plan.mem_free(b_)
-            plan.destroy()
-            checked += 1
+            # NVLINK_FUSED also runs with the FFT <-> exchange stage overlap (3 uneven chunks)
+            for overlap in ([1, 3] if backend == Backend.NVLINK_FUSED else [1]):
+                nd = len(dims)
+                cfg = Config(backend=backend, enable_z_slab=False)
+                plan = cls(dims, comm=comm, precision=prec, executor=Executor.CUFFT, config=cfg)
+                plan.set_overlap(overlap)
+                G = P.global_array(dims, rdt, kind="random")
+                ins, inc, outs, outc, alloc = plan.local_sizes
+                xin = L.Pencil(1, ins, inc)
+                x = P.pencil_slice(G, xin)
+                rev = tuple(range(nd - 1, -1, -1))
+                if cls is PlanR2C:
+                    spec = np.fft.rfftn(G.astype(np.float64).transpose(rev)).transpose(rev)
+                else:
+                    spec = np.fft.fftn(G.astype(np.complex128))
+                outp = L.Pencil(nd, outs, outc)
+                want = P.pencil_slice(np.asfortranarray(spec), outp)
+                ab, at = dev_buf(plan, plan.alloc_bytes, x)
+                bb, bt = dev_buf(plan, plan.alloc_bytes)
+                cb, ct = dev_buf(plan, plan.alloc_bytes)
+                dist.barrier()
+                plan.execute(at, bt, Execute.FORWARD)
+                sync(plan)
+                got = host(bt, cdt, want.size).astype(np.complex128)
+                num = np.array([np.linalg.norm(got - want) ** 2, np.linalg.norm(want) ** 2])
+                tt = torch.from_numpy(num).cuda()
+                dist.all_reduce(tt)
+                rel = float(torch.sqrt(tt[0] / tt[1]))
+                assert rel <= tol, (backend.name, cls.__name__, rel)
+                if overlap > 1:  # at least the first FFT -> transposition stage ran chunked
+                    assert plan.overlapped_stages >= 1, (cls.__name__, dims, plan.overlapped_stages)
+                else:
+                    assert plan.overlapped_stages == 0
+                plan.execute(bt, ct, Execute.BACKWARD)
+                sync(plan)
+                back = host(ct, rdt, x.size).astype(np.complex128) / np.prod(dims)
+                eps = np.finfo(np.float64 if prec == Precision.DOUBLE else np.float32).eps
+                assert np.max(np.abs(back - x)) <= 5 * np.log2(float(np.prod(dims))) * 2 * eps
+                for b_ in (ab, bb, cb):
+                    plan.mem_free(b_)
+                plan.destroy()
+                checked += 1
 
         # bricks -> pencils -> bricks with uneven cuts (needs an even number of ranks)
         if world % 2 == 0:
@@ -181,7 +190,7 @@ def main():
     # DTFFT_PATIENT: timed backend choice (run_autotune_backend), then a correct transposition
     plan = PlanC2C([128, 64, 96], comm=comm, effort=Effort.PATIENT, config=Config(enable_z_slab=False))
     picked = plan.backend
-    assert picked in backends
+    assert picked in (Backend.NCCL, Backend.NCCL_PIPELINED, Backend.NVLINK_FUSED)
     G = P.global_array([128, 64, 96], np.complex128)
     xp, yp = oracle_pencil(plan.get_pencil(Layout.X_PENCILS)), oracle_pencil(plan.get_pencil(Layout.Y_PENCILS))
     src, want = P.pencil_slice(G, xp), P.pencil_slice(G, yp)
