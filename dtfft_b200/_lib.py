@@ -121,6 +121,9 @@ def _declare_plan_api(L):
         "dtfftb_plan_get_stats": [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "dtfftb_plan_peer_error": [vp],
         "dtfftb_plan_set_overlap": [vp, C.c_int, C.c_int],
+        "dtfftb_plan_set_graphs": [vp, C.c_int],
+        "dtfftb_plan_get_overlap": [vp, C.POINTER(C.c_int)],
+        "dtfftb_plan_get_graph_replays": [vp, C.POINTER(C.c_int64)],
         "dtfftb_plan_get_overlapped_stages": [vp, C.POINTER(C.c_int64)],
         "dtfftb_plan_create_dry": [C.c_int, C.c_int8, i32p, vp, vp, C.c_int, C.c_int, pvp],
         "dtfftb_plan_describe_exchange": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p,

@@ -52,6 +52,11 @@ public:
     int kernel_launches() const { return launches_; }  // of OUR kernels per execute
     const HandleGeometry& geometry() const { return geo_; }
     void destroy();
+    // Drop the fused kernels cached per destination address (their peer mappings die with the buffer).
+    void forget_buffers() {
+        fused_.clear();
+        fused_chunks_.clear();
+    }
 
     // ---- stage overlap on the NVLINK_FUSED path (no reference counterpart) ----------------
     // The source pencil is cut along its SLOWEST axis into `nchunks` ranges; chunk k can be

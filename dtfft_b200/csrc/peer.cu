@@ -87,12 +87,21 @@ void ipc_close(void* p) {
         }
 }
 
-// One block; thread t handles member t.
+// One block; thread t handles member t.  The epoch lives in device memory and is advanced by the
+// kernel itself, so the launch carries no per-call argument and can be replayed from a CUDA graph.
 __global__ void peer_barrier_kernel(uint64_t* const* __restrict__ peer_flags, uint64_t* __restrict__ my_flags,
-                                    const int* __restrict__ members, int n, int me, size_t row, uint64_t epoch,
-                                    long long timeout_cycles, uint64_t* __restrict__ err) {
+                                    const int* __restrict__ members, int n, int me, size_t row,
+                                    uint64_t* __restrict__ epoch_counter, long long timeout_cycles,
+                                    uint64_t* __restrict__ err) {
+    __shared__ uint64_t s_epoch;
     const int t = threadIdx.x;
+    if (t == 0) {
+        s_epoch = *epoch_counter + 1;
+        *epoch_counter = s_epoch;
+    }
+    __syncthreads();
     if (t >= n) return;
+    const uint64_t epoch = s_epoch;
     const int peer = members[t];
     uint64_t* remote = peer_flags[t] + row + me;
     __threadfence_system();
@@ -272,19 +281,21 @@ int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStre
         if (ce != cudaSuccess) return cuda_error(ce);
         ce = cudaMalloc(&g.d_members, n * sizeof(int));
         if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaMalloc(&g.d_epoch, sizeof(uint64_t));
+        if (ce != cudaSuccess) return cuda_error(ce);
+        cudaMemset(g.d_epoch, 0, sizeof(uint64_t));
         cudaMemcpy(g.d_peer_flags, bases.data(), n * sizeof(uint64_t*), cudaMemcpyHostToDevice);
         cudaMemcpy(g.d_members, members.data(), n * sizeof(int), cudaMemcpyHostToDevice);
         it = groups_.emplace(key, g).first;
     }
     Group& g = it->second;
-    ++g.epoch;
     const int P = world_.size();
     uint64_t* err = flags_ + (size_t)kChannels * P;
     // ~20 s at 2 GHz: a missing peer turns into a sticky error instead of a hung GPU
     const long long timeout = 40ll * 1000 * 1000 * 1000;
     const int threads = ((n + 31) / 32) * 32;
     peer_barrier_kernel<<<1, threads, 0, stream>>>(g.d_peer_flags, flags_, g.d_members, n, world_.rank(),
-                                                   (size_t)channel * P, g.epoch, timeout, err);
+                                                   (size_t)channel * P, g.d_epoch, timeout, err);
     cudaError_t ce = cudaGetLastError();
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
@@ -301,6 +312,7 @@ void PeerRegistry::destroy() {
     for (auto& kv : groups_) {
         if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
         if (kv.second.d_members) cudaFree(kv.second.d_members);
+        if (kv.second.d_epoch) cudaFree(kv.second.d_epoch);
     }
     groups_.clear();
     bool any = false;

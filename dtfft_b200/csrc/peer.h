@@ -63,7 +63,7 @@ private:
         uint64_t** d_peer_flags = nullptr;  // [n] device array: flags base of each member
         int* d_members = nullptr;           // [n] world ranks
         int n = 0;
-        uint64_t epoch = 0;
+        uint64_t* d_epoch = nullptr;        // device-side epoch counter of this group (graph-replayable)
     };
     int open_all(const void* base, size_t offset, Slot& s);
 

@@ -163,8 +163,9 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     if (executor < DTFFT_EXECUTOR_NONE || executor > DTFFT_EXECUTOR_VKFFT) return DTFFT_ERROR_INVALID_EXECUTOR;
     if (executor != DTFFT_EXECUTOR_NONE && executor != DTFFT_EXECUTOR_CUFFT) return DTFFT_ERROR_INVALID_PLATFORM_EXECUTOR;
     precision_ = precision, effort_ = effort, executor_ = executor;
-    if (const char* e = getenv("DTFFTB_OVERLAP_CHUNKS")) overlap_chunks_ = std::max(1, atoi(e));
+    if (const char* e = getenv("DTFFTB_OVERLAP_CHUNKS")) overlap_chunks_ = std::max(1, atoi(e)), overlap_user_set_ = true;
     if (const char* e = getenv("DTFFTB_OVERLAP_CTAS")) overlap_ctas_ = std::max(0, atoi(e));
+    if (const char* e = getenv("DTFFTB_GRAPHS")) graphs_enabled_ = atoi(e) != 0;
     is_transpose_plan_ = executor == DTFFT_EXECUTOR_NONE;
     if (kind == PLAN_R2R) {
         if (!is_transpose_plan_) {
@@ -255,6 +256,11 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     }
     is_aux_alloc_ = false;
     created_ = true;
+    rc = choose_overlap();
+    if (rc) {
+        created_ = false;
+        return rc;
+    }
     log("plan created: %dD %s, grid %dx%dx%d, backend %s%s%s", ndims_,
         kind_ == PLAN_C2C ? "c2c" : kind_ == PLAN_R2C ? "r2c" : "r2r", comm_dims_[0], comm_dims_[1], comm_dims_[2],
         dtfft_get_backend_string((dtfft_backend_t)backend_), is_z_slab_ ? ", Z-slab" : "", is_y_slab_ ? ", Y-slab" : "");
@@ -759,6 +765,68 @@ int Plan::autotune_backend() {
     return DTFFT_SUCCESS;
 }
 
+int Plan::choose_overlap() {
+    // Stage overlap (FFT chunk k+1 || exchange of chunk k) pays when the FFT before an exchange is
+    // long relative to the exchange: measured on 2 and 8 B200 (profiles/r01d_configs_n*.jsonl) it wins
+    // ~8 % on the 16384^2 slab (16384-point transforms) and loses on 512^3 / 1024^3 pencils, whose
+    // short transforms cannot amortise the extra launches.  Every rank must take the same decision
+    // (the backward pencil schedule changes its buffer choreography with it), so the rule only uses
+    // plan-wide quantities; effort >= DTFFT_MEASURE replaces the rule by a timed choice.
+    const int P = comm_.size();
+    const bool applicable = !is_transpose_plan_ && P > 1 && backend_ == BACKEND_NVLINK_FUSED;
+    if (overlap_user_set_) {
+        if (!applicable) overlap_chunks_ = 1;
+        return DTFFT_SUCCESS;
+    }
+    overlap_chunks_ = 1;
+    if (!applicable) return DTFFT_SUCCESS;
+    long long longest = 1, total = 1;
+    for (int d = 0; d < ndims_; ++d) longest = std::max<long long>(longest, dims_[d]), total *= dims_[d];
+    const long long local_bytes = total * base_storage_ / P;
+    if (longest >= 4096 && local_bytes >= (256ll << 20)) overlap_chunks_ = 8;
+    if (effort_ < DTFFT_MEASURE) return DTFFT_SUCCESS;
+
+    // timed choice on scratch buffers: forward + backward execute, max over ranks of the mean
+    const size_t bytes = alloc_bytes();
+    void *a = nullptr, *b = nullptr;
+    int rc = mem_alloc(bytes, &a);
+    if (!rc) rc = mem_alloc(bytes, &b);
+    const bool saved_graphs = graphs_enabled_;
+    graphs_enabled_ = false;
+    int best = 1;
+    double best_ms = 1e30;
+    if (!rc) {
+        cudaMemsetAsync(a, 0, bytes, stream_);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0), cudaEventCreate(&e1);
+        for (int cand : {1, 4, 8}) {
+            overlap_chunks_ = cand;
+            auto pass = [&]() {
+                int r2 = execute(a, b, DTFFT_EXECUTE_FORWARD, nullptr);
+                if (r2) return r2;
+                return execute(b, a, DTFFT_EXECUTE_BACKWARD, nullptr);
+            };
+            for (int i = 0; i < cfg_.n_measure_warmup_iters && !rc; ++i) rc = pass();
+            cudaEventRecord(e0, stream_);
+            for (int i = 0; i < cfg_.n_measure_iters && !rc; ++i) rc = pass();
+            cudaEventRecord(e1, stream_);
+            float t = 0;
+            const bool ok = !rc && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess;
+            const double ms = comm_.max(ok ? (double)t / std::max(1, (int)cfg_.n_measure_iters) : 1e30);
+            log("autotune stage overlap, %d chunk(s): %.4f ms per forward + backward", cand, ms);
+            if (ms < best_ms) best_ms = ms, best = cand;
+            if (rc) break;
+        }
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+    }
+    graphs_enabled_ = saved_graphs;
+    overlap_chunks_ = best;
+    if (b) mem_free(b);
+    if (a) mem_free(a);
+    log("stage overlap: %d chunk(s)", overlap_chunks_);
+    return rc;
+}
+
 int Plan::create_ffts() {
     // alloc_fft_plans + create_c2c_core / create_r2c_internal, dtfft_plan.F90:2221-2284, 2543-2556, 2636-2639
     const int me = comm_.rank(), nd = ndims_;
@@ -935,6 +1003,7 @@ int Plan::mem_free(void* ptr) {
         if (allocs_[i].ptr != ptr) continue;
         Alloc a = allocs_[i];
         allocs_.erase(allocs_.begin() + (long)i);
+        forget_buffer_caches();
         if (a.peer) peers_.unregister_buffer(a.ptr);
         if (a.nccl) {
             if (a.reg) ncclCommDeregister(nccl_, a.reg);
@@ -956,7 +1025,19 @@ int Plan::register_buffer(void* ptr, size_t bytes) {
     return slot >= 0 ? DTFFT_SUCCESS : DTFFTB_ERROR_NOT_REGISTERED;
 }
 
-int Plan::unregister_buffer(void* ptr) { return peers_.unregister_buffer(ptr); }
+int Plan::unregister_buffer(void* ptr) {
+    forget_buffer_caches();
+    return peers_.unregister_buffer(ptr);
+}
+
+// Everything keyed by a buffer ADDRESS (captured graphs, fused kernels holding peer mappings of
+// that address) dies with the buffer: a later allocation may reuse the address with other peers.
+void Plan::forget_buffer_caches() {
+    if (stream_) cudaStreamSynchronize(stream_);
+    drop_graphs();
+    for (auto& kv : handles_) kv.second->forget_buffers();
+    for (auto& kv : rhandles_) kv.second->forget_buffers();
+}
 
 int Plan::check_aux(void* aux, bool from_execute, void** aux1, void** aux2) {
     // dtfft_plan.F90:2286-2331
@@ -1141,6 +1222,66 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     rc = check_aux(aux, true, &a1, &a2);
     if (rc) return rc;
     const bool fwd = execute_type == DTFFT_EXECUTE_FORWARD;
+    if (!graphs_usable()) return execute_schedule(in, out, fwd, a1, a2, inplace);
+
+    // CUDA-graph replay of the whole schedule (no reference counterpart; the reference enqueues
+    // every kernel of every execute from the host).  First call with a given (in, out, aux,
+    // direction): eager, so that every lazily built table / cuFFT plan / barrier group exists.
+    // Second call: captured while it is enqueued.  Later calls: one cudaGraphLaunch.
+    GraphKey key{in, out, a1, fwd};
+    auto it = graphs_.find(key);
+    if (it == graphs_.end()) {
+        if (graphs_.size() >= 16) drop_graphs();
+        it = graphs_.emplace(key, GraphEntry{}).first;
+        return execute_schedule(in, out, fwd, a1, a2, inplace);
+    }
+    GraphEntry& g = it->second;
+    if (g.failed) return execute_schedule(in, out, fwd, a1, a2, inplace);
+    if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            g.failed = true;
+            return execute_schedule(in, out, fwd, a1, a2, inplace);
+        }
+        rc = execute_schedule(in, out, fwd, a1, a2, inplace);
+        ce = cudaStreamEndCapture(stream_, &graph);
+        if (rc == DTFFT_SUCCESS && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != DTFFT_SUCCESS || ce != cudaSuccess || !g.exec) {
+            // nothing was enqueued by the failed capture: run this call eagerly and stop trying
+            cudaGetLastError();
+            g.exec = nullptr;
+            g.failed = true;
+            stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = 0;
+            return execute_schedule(in, out, fwd, a1, a2, inplace);
+        }
+        g.launches = stat_launches_, g.local = stat_local_, g.remote = stat_remote_, g.overlapped = stat_overlapped_;
+    }
+    stat_launches_ = g.launches, stat_local_ = g.local, stat_remote_ = g.remote, stat_overlapped_ = g.overlapped;
+    cudaError_t ce = cudaGraphLaunch(g.exec, stream_);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    ++stat_graph_replays_;
+    return DTFFT_SUCCESS;
+}
+
+bool Plan::graphs_usable() const {
+    if (!graphs_enabled_) return false;
+    // NCCL collectives are left out of graphs (user-buffer registration, proxy threads)
+    auto ok = [](int b) { return b == BACKEND_NONE || b == BACKEND_NVLINK_FUSED; };
+    if (comm_.size() > 1 && !ok(backend_)) return false;
+    if (comm_.size() > 1 && is_reshape_enabled_ && !ok(reshape_backend_)) return false;
+    return true;
+}
+
+void Plan::drop_graphs() {
+    for (auto& kv : graphs_)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs_.clear();
+}
+
+int Plan::execute_schedule(void* in, void* out, bool fwd, void* a1, void* a2, bool inplace) {
     // execute_private, :839-875
     if (ndims_ == 2 || is_y_slab_)
         return is_reshape_enabled_ ? execute_2d_reshape(in, out, fwd, a1, a2) : execute_2d(in, out, fwd, a1, a2);
@@ -1354,6 +1495,7 @@ int Plan::report() const {
 int Plan::destroy() {
     // dtfft_plan.F90:1169-1250
     if (stream_) cudaStreamSynchronize(stream_);
+    drop_graphs();
     if (xfer_stream_) {
         cudaStreamSynchronize(xfer_stream_);
         cudaStreamDestroy(xfer_stream_);

@@ -12,6 +12,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "comm.h"
@@ -115,7 +116,17 @@ public:
     int peer_error() { return peers_.error_state(); }
     // Stage overlap of the cuFFT executor with the NVLINK_FUSED exchange: number of chunks
     // (<= 1 disables) and CTAs of the persistent exchange kernel (0 = one per SM).
-    void set_overlap(int nchunks, int ctas) { overlap_chunks_ = nchunks, overlap_ctas_ = ctas; }
+    void set_overlap(int nchunks, int ctas) {
+        overlap_chunks_ = nchunks, overlap_ctas_ = ctas, overlap_user_set_ = true;
+        drop_graphs();
+    }
+    // dtfft_execute replays a CUDA graph captured on the second call with the same buffers
+    // (single-GPU and NVLINK_FUSED plans; env DTFFTB_GRAPHS=0 disables).
+    void set_graphs(bool on) {
+        graphs_enabled_ = on;
+        drop_graphs();
+    }
+    int64_t graph_replays() const { return stat_graph_replays_; }
     int overlap_chunks() const { return overlap_chunks_; }
     int64_t overlapped_stages() const { return stat_overlapped_; }
 
@@ -150,6 +161,7 @@ private:
     int build_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& into);
     int build_reshape_handles(int backend);
     int autotune_backend();
+    int choose_overlap();
     int time_backend(int backend, double* ms);
     int create_ffts();
     int check_aux(void* aux, bool from_execute, void** aux1, void** aux2);
@@ -160,6 +172,10 @@ private:
     // FFT a -> b followed by the transposition b -> c.  With the NVLINK_FUSED backend the two
     // are pipelined chunk by chunk over two streams (stage overlap); otherwise run back to back.
     int run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void* c, void* aux);
+    int execute_schedule(void* in, void* out, bool fwd, void* a1, void* a2, bool inplace);
+    bool graphs_usable() const;
+    void drop_graphs();
+    void forget_buffer_caches();
     int execute_2d(void* in, void* out, bool fwd, void* aux, void* aux2);
     int execute_z_slab(void* in, void* out, bool fwd, void* aux, bool inplace, void* aux2);
     int execute_generic(void* in, void* out, bool fwd, void* aux, void* aux2);
@@ -213,8 +229,25 @@ private:
     void* aux_ptr_ = nullptr;
     bool is_aux_alloc_ = false;
     int64_t stat_launches_ = 0, stat_local_ = 0, stat_remote_ = 0, stat_overlapped_ = 0;
+    // CUDA-graph replay of dtfft_execute
+    struct GraphKey {
+        const void *in, *out, *aux;
+        bool fwd;
+        bool operator<(const GraphKey& o) const {
+            return std::tie(in, out, aux, fwd) < std::tie(o.in, o.out, o.aux, o.fwd);
+        }
+    };
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        bool failed = false;
+        int64_t launches = 0, local = 0, remote = 0, overlapped = 0;
+    };
+    std::map<GraphKey, GraphEntry> graphs_;
+    bool graphs_enabled_ = true;
+    int64_t stat_graph_replays_ = 0;
     // stage overlap
-    int overlap_chunks_ = 4, overlap_ctas_ = 0;
+    int overlap_chunks_ = 1, overlap_ctas_ = 0;
+    bool overlap_user_set_ = false;
     cudaStream_t xfer_stream_ = nullptr;
     std::vector<cudaEvent_t> chunk_events_;
     cudaEvent_t xfer_done_ = nullptr;

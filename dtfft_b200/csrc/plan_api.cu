@@ -467,6 +467,23 @@ dtfft_error_t dtfftb_plan_set_overlap(dtfft_plan_t plan, int nchunks, int exchan
     P(plan)->set_overlap(nchunks < 1 ? 1 : nchunks, exchange_ctas < 0 ? 0 : exchange_ctas);
     return DTFFT_SUCCESS;
 }
+dtfft_error_t dtfftb_plan_get_overlap(dtfft_plan_t plan, int* nchunks) {
+    PLAN_OR_RETURN(plan);
+    if (!nchunks) return DTFFT_ERROR_INVALID_USAGE;
+    *nchunks = P(plan)->overlap_chunks();
+    return DTFFT_SUCCESS;
+}
+dtfft_error_t dtfftb_plan_set_graphs(dtfft_plan_t plan, int enable) {
+    PLAN_OR_RETURN(plan);
+    P(plan)->set_graphs(enable != 0);
+    return DTFFT_SUCCESS;
+}
+dtfft_error_t dtfftb_plan_get_graph_replays(dtfft_plan_t plan, int64_t* n_replays) {
+    PLAN_OR_RETURN(plan);
+    if (!n_replays) return DTFFT_ERROR_INVALID_USAGE;
+    *n_replays = P(plan)->graph_replays();
+    return DTFFT_SUCCESS;
+}
 dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages) {
     PLAN_OR_RETURN(plan);
     if (!n_stages) return DTFFT_ERROR_INVALID_USAGE;

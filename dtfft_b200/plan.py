@@ -398,6 +398,22 @@ class Plan:
         _check(_lib.lib().dtfftb_plan_set_overlap(self._h, int(nchunks), int(exchange_ctas)), "dtfftb_plan_set_overlap")
 
     @property
+    def overlap_chunks(self) -> int:
+        n = C.c_int(0)
+        _check(_lib.lib().dtfftb_plan_get_overlap(self._h, C.byref(n)), "dtfftb_plan_get_overlap")
+        return n.value
+
+    def set_graphs(self, enable: bool):
+        """CUDA-graph replay of execute (extension, see dtfftb_plan_set_graphs)."""
+        _check(_lib.lib().dtfftb_plan_set_graphs(self._h, int(bool(enable))), "dtfftb_plan_set_graphs")
+
+    @property
+    def graph_replays(self) -> int:
+        n = C.c_int64(0)
+        _check(_lib.lib().dtfftb_plan_get_graph_replays(self._h, C.byref(n)), "dtfftb_plan_get_graph_replays")
+        return n.value
+
+    @property
     def overlapped_stages(self) -> int:
         n = C.c_int64(0)
         _check(_lib.lib().dtfftb_plan_get_overlapped_stages(self._h, C.byref(n)), "dtfftb_plan_get_overlapped_stages")

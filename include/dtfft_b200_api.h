@@ -301,9 +301,19 @@ int dtfftb_plan_peer_error(dtfft_plan_t plan);
  * (extension; the reference serialises FFT and exchange on one stream, src/dtfft_plan.F90:1057-1101):
  * the FFT before a transposition is cut into `nchunks` ranges of its slowest axis and chunk k is
  * stored to the peers on a second stream while chunk k+1 is transformed.  nchunks <= 1 disables;
- * `exchange_ctas` = CTAs of the persistent exchange kernel (0 = one per SM).  Default: 4 chunks
- * (env DTFFTB_OVERLAP_CHUNKS / DTFFTB_OVERLAP_CTAS).  Must be set identically on every rank. */
+ * `exchange_ctas` = CTAs of the persistent exchange kernel (0 = one per SM).  Default: a plan-wide
+ * rule at DTFFT_ESTIMATE (8 chunks when the longest transform has >= 4096 points and the local array
+ * is >= 256 MiB, else off), a timed choice among {1, 4, 8} at effort >= DTFFT_MEASURE; the env
+ * variables DTFFTB_OVERLAP_CHUNKS / DTFFTB_OVERLAP_CTAS and this call override both.  Must be set
+ * identically on every rank. */
 dtfft_error_t dtfftb_plan_set_overlap(dtfft_plan_t plan, int nchunks, int exchange_ctas);
+dtfft_error_t dtfftb_plan_get_overlap(dtfft_plan_t plan, int* nchunks);
+/* dtfft_execute replays a CUDA graph: the first call with a given (in, out, aux, direction) runs
+ * eagerly, the second is captured while it is enqueued, later ones are one cudaGraphLaunch
+ * (extension; single-GPU and NVLINK_FUSED plans, env DTFFTB_GRAPHS=0 disables).  Freeing or
+ * unregistering a buffer drops the graphs. */
+dtfft_error_t dtfftb_plan_set_graphs(dtfft_plan_t plan, int enable);
+dtfft_error_t dtfftb_plan_get_graph_replays(dtfft_plan_t plan, int64_t* n_replays);
 /* Number of FFT+transposition stages of the last dtfft_execute that ran overlapped. */
 dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages);
 

@@ -117,6 +117,18 @@ def main():
                 dist.all_reduce(tt)
                 rel = float(torch.sqrt(tt[0] / tt[1]))
                 assert rel <= tol, (backend.name, cls.__name__, rel)
+                # the third call with the same buffers replays the CUDA graph captured during the second
+                if backend == Backend.NVLINK_FUSED:
+                    for _ in range(2):
+                        at[: x.nbytes] = torch.from_numpy(np.ascontiguousarray(x).view(np.uint8).copy()).cuda()
+                        bt.fill_(0xAB)
+                        torch.cuda.synchronize()
+                        dist.barrier()
+                        plan.execute(at, bt, Execute.FORWARD)
+                        sync(plan)
+                    assert plan.graph_replays >= 1, plan.graph_replays
+                    got3 = host(bt, cdt, want.size).astype(np.complex128)
+                    assert np.array_equal(got3, got), "graph replay differs from the eager run"
                 if overlap > 1:  # at least the first FFT -> transposition stage ran chunked
                     assert plan.overlapped_stages >= 1, (cls.__name__, dims, plan.overlapped_stages)
                 else:
@@ -203,9 +215,32 @@ def main():
     plan.mem_free(ab)
     plan.mem_free(bb)
     plan.destroy()
+
+    # DTFFT_MEASURE on an FFT plan with the NVLINK_FUSED backend: timed choice of the stage overlap
+    # (choose_overlap), then a forward + backward round trip within the reference's tolerance
+    dims = [128, 64, 96]
+    plan = PlanC2C(dims, comm=comm, effort=Effort.MEASURE, executor=Executor.CUFFT,
+                   config=Config(enable_z_slab=False, backend=Backend.NVLINK_FUSED))
+    assert plan.overlap_chunks in (1, 4, 8), plan.overlap_chunks
+    G = P.global_array(dims, np.complex128, kind="random")
+    ins, inc, outs, outc, alloc = plan.local_sizes
+    x = P.pencil_slice(G, L.Pencil(1, ins, inc))
+    ab, at = dev_buf(plan, plan.alloc_bytes, x)
+    bb, bt = dev_buf(plan, plan.alloc_bytes)
+    cb, ct = dev_buf(plan, plan.alloc_bytes)
+    dist.barrier()
+    plan.execute(at, bt, Execute.FORWARD)
+    plan.execute(bt, ct, Execute.BACKWARD)
+    sync(plan)
+    back = host(ct, np.complex128, x.size) / np.prod(dims)
+    assert np.max(np.abs(back - x)) <= 5 * np.log2(float(np.prod(dims))) * 2 * np.finfo(np.float64).eps
+    tuned = plan.overlap_chunks
+    for b_ in (ab, bb, cb):
+        plan.mem_free(b_)
+    plan.destroy()
     Config()._commit()
     dist.barrier()
-    print(f"rank {rank}/{world}: multi-GPU plan checks OK ({checked} cases, PATIENT picked {picked.name})", flush=True)
+    print(f"rank {rank}/{world}: multi-GPU plan checks OK ({checked} cases, PATIENT picked {picked.name}, MEASURE overlap {tuned})", flush=True)
     dist.destroy_process_group()
 
 

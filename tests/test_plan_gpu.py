@@ -83,6 +83,46 @@ def test_transpose_only_execute_round_trip(cuda, dims, z_slab):
     Config()._commit()
 
 
+@pytest.mark.parametrize("dims", [[129, 99, 33], [90, 57]])
+def test_execute_graph_replay_is_bit_identical(cuda, dims):
+    """The second dtfft_execute with the same buffers is captured into a CUDA graph and later calls
+    replay it: results must equal the eager first call bit for bit (transposes and cuFFT alike),
+    and freeing a buffer must drop the graphs."""
+    torch = cuda
+    from dtfft_b200.plan import Executor
+
+    for executor in (Executor.NONE, Executor.CUFFT):
+        plan = PlanC2C(dims, executor=executor, config=Config(enable_z_slab=False))
+        nd = len(dims)
+        G = P.global_array(dims, np.complex128, kind="random")
+        x = P.pencil_slice(G, L.make_pencils(dims, [1] * nd, 0)[0])
+        hx = torch.from_numpy(x.view(np.uint8).copy())
+        ba, bb = plan.mem_alloc(plan.alloc_bytes), plan.mem_alloc(plan.alloc_bytes)
+        a, b = torch.as_tensor(ba, device="cuda"), torch.as_tensor(bb, device="cuda")
+        outs = []
+        for i in range(4):
+            a[: hx.numel()] = hx.cuda()
+            b.fill_(0xAB)
+            torch.cuda.synchronize()
+            plan.execute(a, b, Execute.FORWARD)
+            sync(torch, plan)
+            outs.append(b.cpu().numpy().copy())
+        assert plan.graph_replays >= 2
+        for o in outs[1:]:
+            assert np.array_equal(o, outs[0])
+        plan.set_graphs(False)
+        a[: hx.numel()] = hx.cuda()
+        torch.cuda.synchronize()
+        n0 = plan.graph_replays
+        plan.execute(a, b, Execute.FORWARD)
+        sync(torch, plan)
+        assert plan.graph_replays == n0 and np.array_equal(b.cpu().numpy(), outs[0])
+        plan.mem_free(ba)
+        plan.mem_free(bb)
+        plan.destroy()
+    Config()._commit()
+
+
 @pytest.mark.parametrize("dims", [[64, 48, 40], [129, 99, 33], [64, 96], [512, 64, 32]])
 @pytest.mark.parametrize("prec,cdtype,tol", [(Precision.DOUBLE, np.complex128, 1e-12), (Precision.SINGLE, np.complex64, 1e-5)])
 @pytest.mark.parametrize("z_slab", [True, False])

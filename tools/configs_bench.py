@@ -129,7 +129,8 @@ def main():
                     p1 = {2: 2, 4: 2, 8: 4}.get(world, world)
                     pcomm = TorchComm(cart_dims=[1, p1, world // p1])
                 plan = cls(dims, comm=pcomm, precision=prec, executor=Executor.CUFFT, config=cfg)
-                plan.set_overlap(ov)
+                if ov > 0:  # 0 = the plan's own choice (rule at ESTIMATE, timed at MEASURE)
+                    plan.set_overlap(ov)
                 ins, inc, outs, outc, alloc = plan.local_sizes
                 nbytes = plan.alloc_bytes
                 bufs = [plan.mem_alloc(nbytes) for _ in range(3)]
@@ -205,9 +206,9 @@ def main():
 
                 ms = timed(plan, stream, cyc, args.iters)
                 emit({"config": name, "dims": dims, "n_gpus": world, "grid": plan.grid_dims, "backend": plan.backend.name,
-                      "overlap_chunks": ov, "overlapped_stages_per_execute": stages, "fwd_bwd_ms": ms,
+                      "overlap_chunks": plan.overlap_chunks, "overlap_requested": ov, "overlapped_stages_per_execute": stages, "fwd_bwd_ms": ms,
                       "spike_rel_l2": rel, "spike_ok": ok_spike, "round_trip_max_err": maxerr, "round_trip_bound": bound,
-                      "round_trip_ok": ok_rt, "z_slab": plan.z_slab_enabled, "peer_error": plan.peer_error()})
+                      "round_trip_ok": ok_rt, "z_slab": plan.z_slab_enabled, "graph_replays": plan.graph_replays, "peer_error": plan.peer_error()})
                 assert ok_spike and ok_rt, (name, bname, ov, rel, maxerr)
                 for x_ in bufs:
                     plan.mem_free(x_)
@@ -300,7 +301,7 @@ def main():
                   "backward_bit_exact": ok_bwd, "local_bytes_per_execute": st["local_bytes"],
                   "remote_bytes_per_execute": st["remote_bytes"], "launches_per_execute": st["kernel_launches"],
                   "effective_GBps": 2 * 2 * st["local_bytes"] * world / (ms * 1e-3) / 1e9,
-                  "peer_error": plan.peer_error()})
+                  "graph_replays": plan.graph_replays, "peer_error": plan.peer_error()})
             assert ok_fwd and ok_bwd, ("c5", bname)
             for x_ in bufs + ([aux] if aux is not None else []):
                 plan.mem_free(x_)
