@@ -288,10 +288,17 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("transpose_tiles_kernel_bytes_per_launch")
         except Exception:
             traffic = None
+    # name the kernel instantiation from the kernel plugin itself (B200 tile table, kernel_object.cu)
+    from dtfft_b200.kernel import KERNEL_PERMUTE_FORWARD, Kernel
+
+    probe = Kernel().create([64, 64, 64], 0, ES, KERNEL_PERMUTE_FORWARD)
+    ki = probe.info()
+    probe.destroy()
+    tname = f"transpose_tiles_kernel<uint4,{ki['tile_a'] // 32},{ki['tile_b'] // 32},{ki['threads'] // 32}>"
     if world == 1:
-        kernel_name = "transpose_tiles_kernel<uint4,2,2,8> (one launch per transposition)"
+        kernel_name = f"{tname} (one launch per transposition)"
     elif R["backend"] == "NVLINK_FUSED":
-        kernel_name = "transpose_tiles_kernel<uint4,2,2,8> with peer-mapped destinations (+2 peer_barrier_kernel)"
+        kernel_name = f"{tname} with peer-mapped destinations (+2 peer_barrier_kernel)"
     else:
         kernel_name = "transpose_tiles_kernel (pack) + ncclSend/Recv + rows_copy_kernel (unpack)"
 
@@ -402,7 +409,7 @@ def run_ours(args):
                 "how": "pinned host -> device copy of every step's input, dtfft_execute FORWARD + BACKWARD, device -> "
                        "pinned host copy of the result; two buffer sets so the D2H of step k overlaps the H2D of step k+1",
                 "serial_ms_per_step": e2e_serial_ms, "serial_value": CYCLE_BYTES / (e2e_serial_ms * 1e-3) / 1e9},
-        "gpu_launches": R["launches"],
+        "gpu_launches": R["launches"], "graph_replays": plan.graph_replays,
         "clocks": R["clocks"],
     }
     if world > 1:
