@@ -1233,7 +1233,12 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     if (it == graphs_.end()) {
         if (graphs_.size() >= 16) drop_graphs();
         it = graphs_.emplace(key, GraphEntry{}).first;
-        return execute_schedule(in, out, fwd, a1, a2, inplace);
+        rc = execute_schedule(in, out, fwd, a1, a2, inplace);
+        // A schedule with overlapped stages stays eager: measured on 2 B200 (profiles/r01f_configs_auto_n2.jsonl
+        // vs r01d_configs_n2.jsonl, 16384^2 slab) the two-stream pipeline loses its overlap when replayed as
+        // graph branches (9.41 ms vs 8.55 ms eager), and such schedules are long enough not to be launch-bound.
+        if (stat_overlapped_ > 0) it->second.failed = true;
+        return rc;
     }
     GraphEntry& g = it->second;
     if (g.failed) return execute_schedule(in, out, fwd, a1, a2, inplace);

@@ -126,7 +126,10 @@ def main():
                         dist.barrier()
                         plan.execute(at, bt, Execute.FORWARD)
                         sync(plan)
-                    assert plan.graph_replays >= 1, plan.graph_replays
+                    if plan.overlapped_stages == 0:  # schedules with overlapped stages stay eager
+                        assert plan.graph_replays >= 1, plan.graph_replays
+                    else:
+                        assert plan.graph_replays == 0
                     got3 = host(bt, cdt, want.size).astype(np.complex128)
                     assert np.array_equal(got3, got), "graph replay differs from the eager run"
                 if overlap > 1:  # at least the first FFT -> transposition stage ran chunked
