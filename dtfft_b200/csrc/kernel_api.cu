@@ -5,11 +5,9 @@
 
 #include "../../include/dtfft_b200.h"
 #include "errors.h"
+#include "c_handles.h"
 #include "kernel_object.h"
 
-struct dtfftb_kernel_s {
-    dtfftb::Kernel k;
-};
 
 extern "C" {
 

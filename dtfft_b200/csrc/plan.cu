@@ -52,26 +52,38 @@ int FftExecutor::make_plans(long long how_many, Handles* h) {
 int FftExecutor::create(int fft_rank, bool r2c, int precision, const Pencil* real, const Pencil& cpx,
                         cudaStream_t stream) {
     // abstract_executor%create, src/dtfft_abstract_executor.F90:115-216
+    int n[2] = {1, 1}, inembed[2] = {1, 1}, onembed[2] = {1, 1};
+    const Pencil& base = r2c ? *real : cpx;
+    if (fft_rank == 1) {
+        n[0] = base.counts[0];
+        inembed[0] = n[0];
+        onembed[0] = cpx.counts[0];
+    } else {
+        n[0] = base.counts[1], n[1] = base.counts[0];
+        inembed[0] = n[0], inembed[1] = n[1];
+        onembed[0] = cpx.counts[1], onembed[1] = cpx.counts[0];
+    }
+    long long idist = 1, odist = 1;
+    for (int i = 0; i < fft_rank; ++i) idist *= inembed[i], odist *= onembed[i];
+    const long long how_many = (idist == 0 || base.size() == 0) ? 0 : base.size() / idist;
+    return create_raw(fft_rank, r2c, precision, idist, odist, how_many, n, inembed, onembed, stream);
+}
+
+int FftExecutor::create_raw(int fft_rank, bool r2c, int precision, long long idist, long long odist, long long how_many,
+                            const int* fft_sizes, const int* inembed, const int* onembed, cudaStream_t stream) {
     destroy();
+    if (fft_rank != 1 && fft_rank != 2) return DTFFTB_ERROR_INTERNAL;
     r2c_ = r2c;
     rank_ = fft_rank;
     precision_ = precision;
     stream_ = stream;
-    const Pencil& base = r2c ? *real : cpx;
-    if (fft_rank == 1) {
-        n_[0] = base.counts[0];
-        inembed_[0] = n_[0];
-        onembed_[0] = cpx.counts[0];
-    } else {
-        n_[0] = base.counts[1], n_[1] = base.counts[0];
-        inembed_[0] = n_[0], inembed_[1] = n_[1];
-        onembed_[0] = cpx.counts[1], onembed_[1] = cpx.counts[0];
+    for (int i = 0; i < fft_rank; ++i) n_[i] = fft_sizes[i], inembed_[i] = inembed[i], onembed_[i] = onembed[i];
+    idist_ = idist, odist_ = odist;
+    how_many_ = how_many;
+    if (idist_ <= 0 || how_many_ <= 0) {  // rank without data: no FFT needed
+        how_many_ = 0;
+        return DTFFT_SUCCESS;
     }
-    idist_ = 1, odist_ = 1;
-    for (int i = 0; i < fft_rank; ++i) idist_ *= inembed_[i], odist_ *= onembed_[i];
-    if (idist_ == 0 || base.size() == 0) return DTFFT_SUCCESS;  // rank without data: no FFT needed
-    how_many_ = base.size() / idist_;
-    if (how_many_ == 0) return DTFFT_SUCCESS;
     const size_t cb = precision == DTFFT_SINGLE ? 8 : 16;
     out_bytes_ = cb;
     in_bytes_ = r2c ? cb / 2 : cb;

@@ -46,6 +46,11 @@ public:
     ~FftExecutor() { destroy(); }
     // fft_rank 1 or 2 along the fastest axis (axes) of `cpx` (and `real` for R2C)
     int create(int fft_rank, bool r2c, int precision, const Pencil* real, const Pencil& cpx, cudaStream_t stream);
+    // The deferred create_private of abstract_executor, argument for argument
+    // (src/dtfft_abstract_executor.F90:67-84): transform sizes slowest first like cuFFT, unit
+    // stride, `idist` / `odist` elements between consecutive transforms.
+    int create_raw(int fft_rank, bool r2c, int precision, long long idist, long long odist, long long how_many,
+                   const int* fft_sizes, const int* inembed, const int* onembed, cudaStream_t stream);
     int execute(void* a, void* b, int sign);  // sign -1 forward, +1 backward
     // Stage overlap (no reference counterpart): a contiguous range of the batch,
     // [first, first + count) of how_many() transforms.  prepare_range builds the cuFFT plan of a

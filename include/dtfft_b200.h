@@ -123,6 +123,57 @@ int dtfftb_kernel_set_tile(dtfftb_kernel_t kernel, int ka, int kb, int rows);
 int dtfftb_kernel_autotune(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
                            int n_iters, float* best_ms);
 
+/* ------------------------------------------------------------------------------------
+ * Exchange-backend plugin surface -- replaces backend_nccl (src/dtfft_backend_nccl.F90:38-134)
+ * behind the deferred interface of abstract_backend (create_private / execute_private /
+ * destroy_private, src/dtfft_abstract_backend.F90:114-139) together with the part of
+ * abstract_backend%create / execute it inherits (:143-343: float-unit conversion, aux sizing,
+ * self-copy on a second stream with event fork / join).  The NCCL communicator comes from
+ * dtfftb_nccl_comm_create, the replacement of backend_helper%create (:395-457).
+ * ---------------------------------------------------------------------------------- */
+typedef struct dtfftb_backend_s* dtfftb_backend_t;
+typedef struct dtfftb_executor_s* dtfftb_executor_t;
+
+/* One NCCL communicator over the process group `comm` (NULL = 1 rank); `*nccl_comm` is an
+ * ncclComm_t.  Collective. */
+int dtfftb_nccl_comm_create(const dtfftb_comm_t* comm, void** nccl_comm);
+int dtfftb_nccl_comm_destroy(void** nccl_comm);
+
+/*   backend_type   DTFFT_BACKEND_NCCL (24) or DTFFT_BACKEND_NCCL_PIPELINED (27)
+ *   comm_rank/size my index in, and size of, the 1-D communicator of the transposition
+ *   comm_mapping   [comm_size] member -> rank in `nccl_comm` (comm_mappings, :432-441); NULL = identity
+ *   *_displs/_counts  [comm_size] in ELEMENTS of `base_storage` bytes, displacements 0-based
+ *                  (the reference keeps them 1-based in float units internally, :160-183) */
+int dtfftb_backend_create(dtfftb_backend_t* backend, int backend_type, void* nccl_comm, int comm_rank, int comm_size,
+                          const int32_t* comm_mapping, const int64_t* send_displs, const int64_t* send_counts,
+                          const int64_t* recv_displs, const int64_t* recv_counts, int64_t base_storage);
+/* Pipelined flavour: the per-peer unpack kernel the backend launches as blocks arrive
+ * (abstract_backend%set_unpack_kernel, :345-352).  The kernel stays owned by the caller. */
+int dtfftb_backend_set_unpack_kernel(dtfftb_backend_t backend, dtfftb_kernel_t unpack_kernel);
+/* Workspace the pipelined flavour needs in `aux` (0 for the plain one), :196-201. */
+int dtfftb_backend_get_aux_bytes(dtfftb_backend_t backend, int64_t* aux_bytes);
+/* abstract_backend%execute (:223-293) + backend_nccl%execute_private (src/dtfft_backend_nccl.F90:65-134):
+ * plain: grouped ncclSend / ncclRecv all-to-all(v) `in` -> `out`; pipelined: self block copied and
+ * unpacked on a second stream, peers received into `aux` and unpacked into `out` one by one. */
+int dtfftb_backend_execute(dtfftb_backend_t backend, void* in, void* out, void* stream, void* aux);
+int dtfftb_backend_destroy(dtfftb_backend_t* backend);
+
+/* ------------------------------------------------------------------------------------
+ * FFT-executor plugin surface -- replaces cufft_executor
+ * (src/interfaces/fft/cufft/dtfft_executor_cufft_m.F90:52-125) behind the deferred interface of
+ * abstract_executor (src/dtfft_abstract_executor.F90:67-112), argument for argument:
+ *   fft_rank 1 or 2; fft_type 0 = c2c, 1 = r2c (2 = r2r -> DTFFT_ERROR_R2R_FFT_NOT_SUPPORTED);
+ *   precision dtfft_precision_t; idist / odist elements between consecutive transforms of the
+ *   input / output; how_many transforms; fft_sizes / inembed / onembed [fft_rank], slowest first.
+ * Batched along the fastest dimension, unit stride, unnormalised; execute(a, b, sign): sign -1
+ * forward, +1 backward (c2r for r2c plans).  how_many == 0 gives a valid no-op handle.
+ * ---------------------------------------------------------------------------------- */
+int dtfftb_executor_create(dtfftb_executor_t* executor, int fft_rank, int fft_type, int precision, int32_t idist,
+                           int32_t odist, int32_t how_many, const int32_t* fft_sizes, const int32_t* inembed,
+                           const int32_t* onembed, void* stream);
+int dtfftb_executor_execute(dtfftb_executor_t executor, void* a, void* b, int sign);
+int dtfftb_executor_destroy(dtfftb_executor_t* executor);
+
 /* Library info */
 const char* dtfftb_version(void);
 /* 1 if a CUDA device is usable in this process, else 0 (never falls back to CPU). */
