@@ -76,6 +76,25 @@ GridChoice choose_grid(int ndims, const int32_t* dims, int comm_size, bool cuda,
     return g;
 }
 
+std::vector<std::pair<int, int>> grid_candidates(const int32_t* dims, int comm_size) {
+    std::vector<std::pair<int, int>> out;
+    int dperm[3][3], cperm[3][3];
+    permutations(3, dperm, cperm);
+    auto valid = [&](int g1, int g2) {
+        const int32_t cd[3] = {1, g1, g2};
+        for (int d = 0; d < 3; ++d)
+            if (dims[dperm[d][1]] < cd[cperm[d][1]] || dims[dperm[d][2]] < cd[cperm[d][2]]) return false;
+        return true;
+    };
+    for (int i = 1; (long long)i * i <= comm_size; ++i) {
+        if (comm_size % i) continue;
+        const int j = comm_size / i;
+        if (valid(i, j)) out.emplace_back(i, j);
+        if (i != j && valid(j, i)) out.emplace_back(j, i);
+    }
+    return out;
+}
+
 void cart_coords(int rank, int ndims, const int32_t* comm_dims, int32_t* coords) {
     for (int d = ndims - 1; d >= 0; --d) {
         coords[d] = rank % comm_dims[d];

@@ -11,6 +11,7 @@
 // lists into the world.
 #pragma once
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 namespace dtfftb {
@@ -45,6 +46,12 @@ struct GridChoice {
 };
 GridChoice choose_grid(int ndims, const int32_t* dims, int comm_size, bool cuda, bool z_slab_enabled,
                        bool y_slab_enabled);
+
+// Process grids 1 x g1 x g2 tried by the DTFFT_MEASURE / DTFFT_PATIENT grid search, in the
+// reference's order (autotune_grid_decomposition, src/dtfft_transpose_plan.F90:456-500: for every
+// divisor i <= sqrt(P): (i, P/i) then (P/i, i)), minus the grids autotune_grid rejects because a
+// pencil would have fewer points than ranks along a split axis (:600-607).
+std::vector<std::pair<int, int>> grid_candidates(const int32_t* dims, int comm_size);
 
 void cart_coords(int rank, int ndims, const int32_t* comm_dims, int32_t* coords);
 int cart_rank(int ndims, const int32_t* comm_dims, const int32_t* coords);

@@ -246,7 +246,14 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
         rc = init_nccl();
         if (rc) return rc;
     }
-    if (P > 1 && effort_ >= DTFFT_PATIENT) {  // run_autotune_backend, transpose_plan.F90:634-855
+    // grid search applies to default 3-D decompositions only (transpose_plan.F90:230-262)
+    bool grid_search = P > 1 && ndims_ == 3 && !has_user_pencil_ && !is_z_slab_ && !is_y_slab_ &&
+                       !(comm_.raw() && comm_.raw()->cart_ndims > 0) && effort_ >= DTFFT_MEASURE;
+    if (const char* e = getenv("DTFFTB_GRID_SEARCH")) grid_search = grid_search && atoi(e) != 0;
+    if (grid_search) {
+        rc = autotune_grid(effort_ >= DTFFT_PATIENT);
+        if (rc) return rc;
+    } else if (P > 1 && effort_ >= DTFFT_PATIENT) {  // run_autotune_backend, transpose_plan.F90:634-855
         rc = autotune_backend();
         if (rc) return rc;
     }
@@ -759,10 +766,59 @@ int Plan::time_backend(int backend, double* ms) {
     return rc;
 }
 
-int Plan::autotune_backend() {
+std::vector<int> Plan::backend_candidates() const {
     std::vector<int> cands = {BACKEND_NCCL};
     if (cfg_.enable_pipelined_backends) cands.push_back(BACKEND_NCCL_PIPELINED);
     if (cfg_.enable_fused_backends && peers_.available()) cands.push_back(BACKEND_NVLINK_FUSED);
+    return cands;
+}
+
+void Plan::set_grid(int g1, int g2) {
+    comm_dims_[0] = 1, comm_dims_[1] = g1, comm_dims_[2] = g2;
+    const int P = comm_.size();
+    coords_.assign((size_t)P, {0, 0, 0});
+    for (int r = 0; r < P; ++r) {
+        int32_t c[3] = {0, 0, 0};
+        cart_coords(r, ndims_, comm_dims_, c);
+        coords_[(size_t)r] = {c[0], c[1], c[2]};
+    }
+    build_pencils();
+}
+
+int Plan::dry_set_grid(int g1, int g2) {
+    if (!created_ || !dry_ || ndims_ != 3 || has_user_pencil_) return DTFFT_ERROR_INVALID_USAGE;
+    if (g1 < 1 || g2 < 1 || (long long)g1 * g2 != comm_.size()) return DTFFT_ERROR_INVALID_COMM_DIMS;
+    is_z_slab_ = is_y_slab_ = false;
+    set_grid(g1, g2);
+    return DTFFT_SUCCESS;
+}
+
+int Plan::autotune_grid(bool all_backends) {
+    const int saved1 = comm_dims_[1], saved2 = comm_dims_[2];
+    const std::vector<std::pair<int, int>> grids = grid_candidates(dims_, comm_.size());
+    const std::vector<int> backends = all_backends ? backend_candidates() : std::vector<int>{backend_};
+    double best = 1e30;
+    int best_b = backend_, best1 = saved1, best2 = saved2;
+    for (const auto& g : grids) {
+        set_grid(g.first, g.second);
+        for (int b : backends) {
+            double ms = 1e30;
+            int rc = time_backend(b, &ms);
+            if (rc) return rc;
+            log("autotune grid 1x%dx%d, backend %s: %.4f ms", g.first, g.second, dtfft_get_backend_string((dtfft_backend_t)b), ms);
+            if (ms < best) best = ms, best_b = b, best1 = g.first, best2 = g.second;
+        }
+    }
+    // nothing could be timed (no valid grid): keep the default decomposition (transpose_plan.F90:502-525)
+    set_grid(best1, best2);
+    backend_ = best_b;
+    log("DTFFT_MEASURE: selected process grid 1x%dx%d", best1, best2);
+    if (all_backends) log("DTFFT_PATIENT: selected backend is %s", dtfft_get_backend_string((dtfft_backend_t)backend_));
+    return DTFFT_SUCCESS;
+}
+
+int Plan::autotune_backend() {
+    const std::vector<int> cands = backend_candidates();
     double best = 1e30;
     int best_b = backend_;
     for (int b : cands) {

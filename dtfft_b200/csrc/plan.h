@@ -119,6 +119,9 @@ public:
         *launches = stat_launches_, *local_bytes = stat_local_, *remote_bytes = stat_remote_;
     }
     int peer_error() { return peers_.error_state(); }
+    // Host-only test hook (dry plans): switch a default 3-D decomposition to the grid 1 x g1 x g2
+    // the way the grid search does.
+    int dry_set_grid(int g1, int g2);
     // Stage overlap of the cuFFT executor with the NVLINK_FUSED exchange: number of chunks
     // (<= 1 disables) and CTAs of the persistent exchange kernel (0 = one per SM).
     void set_overlap(int nchunks, int ctas) {
@@ -166,6 +169,11 @@ private:
     int build_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& into);
     int build_reshape_handles(int backend);
     int autotune_backend();
+    // DTFFT_MEASURE / DTFFT_PATIENT process-grid search (autotune_grid_decomposition,
+    // src/dtfft_transpose_plan.F90:391-540); `all_backends` also times every enabled backend per grid.
+    int autotune_grid(bool all_backends);
+    void set_grid(int g1, int g2);
+    std::vector<int> backend_candidates() const;
     int choose_overlap();
     int time_backend(int backend, double* ms);
     int create_ffts();

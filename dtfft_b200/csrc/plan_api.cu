@@ -509,6 +509,18 @@ dtfft_error_t dtfftb_plan_create_dry(int kind, int8_t ndims, const int32_t* dims
     return DTFFT_SUCCESS;
 }
 
+dtfft_error_t dtfftb_plan_dry_set_grid(dtfft_plan_t plan, int32_t g1, int32_t g2) {
+    PLAN_OR_RETURN(plan);
+    return E(P(plan)->dry_set_grid(g1, g2));
+}
+
+int32_t dtfftb_grid_candidates(const int32_t* dims, int32_t comm_size, int32_t cap, int32_t* grids) {
+    if (!dims || comm_size < 1) return -1;
+    const auto g = dtfftb::grid_candidates(dims, comm_size);
+    for (size_t i = 0; i < g.size() && (int32_t)i < cap && grids; ++i) grids[2 * i] = g[i].first, grids[2 * i + 1] = g[i].second;
+    return (int32_t)g.size();
+}
+
 dtfft_error_t dtfftb_plan_describe_exchange(dtfft_plan_t plan, int type, int32_t cap, int32_t* n_members,
                                             int32_t* my_index, int32_t* members, int32_t* kernels, int32_t* send_nd,
                                             int32_t* recv_nd, int64_t* counts_displs, int64_t* fused_boxes,

@@ -324,6 +324,14 @@ dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_st
 dtfft_error_t dtfftb_plan_create_dry(int kind, int8_t ndims, const int32_t* dims, const dtfft_pencil_t* pencil,
                                      dtfft_comm_t comm, dtfft_precision_t precision, dtfft_executor_t executor,
                                      dtfft_plan_t* plan);
+/* Process grids 1 x g1 x g2 the DTFFT_MEASURE / DTFFT_PATIENT grid search times for a default 3-D
+ * decomposition (autotune_grid_decomposition + the validity rule of autotune_grid,
+ * src/dtfft_transpose_plan.F90:456-500, 600-607), in search order: pairs (g1, g2) written to
+ * `grids` (up to `cap` pairs); returns their number.  Host-only. */
+int32_t dtfftb_grid_candidates(const int32_t* dims, int32_t comm_size, int32_t cap, int32_t* grids);
+/* Dry plans only: re-decompose a default 3-D plan on the grid 1 x g1 x g2 exactly as the grid
+ * search does between two timings (test hook for the host logic). */
+dtfft_error_t dtfftb_plan_dry_set_grid(dtfft_plan_t plan, int32_t g1, int32_t g2);
 /* Exchange geometry of transposition / reshape `type` on this rank (works on dry and real plans).
  * All output arrays are optional (NULL) and hold `cap` peers at most; *n_members is always set.
  *   members[P]        world ranks of the 1-D communicator

@@ -334,3 +334,64 @@ def test_create_argument_validation():
     assert code(lambda: Config(backend=22)._commit()) == 402
     assert code(lambda: Config(backend=77)._commit()) == 202
     Config()._commit()
+
+
+def _grid_candidates(dims, nranks):
+    import ctypes as C
+
+    from dtfft_b200 import _lib
+
+    L_ = _lib.lib()
+    L_.dtfftb_grid_candidates.restype = C.c_int32
+    L_.dtfftb_grid_candidates.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    out = (C.c_int32 * 64)()
+    n = L_.dtfftb_grid_candidates((C.c_int32 * 3)(*dims), nranks, 32, out)
+    return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
+
+def test_grid_search_candidates():
+    """Grids tried by the DTFFT_MEASURE / DTFFT_PATIENT search: every divisor pair in the reference's
+    order (src/dtfft_transpose_plan.F90:456-500), minus those with fewer points than ranks along a
+    split axis of any pencil (autotune_grid, :600-607)."""
+    assert _grid_candidates((512, 512, 512), 8) == [(1, 8), (8, 1), (2, 4), (4, 2)]
+    assert _grid_candidates((512, 512, 512), 4) == [(1, 4), (4, 1), (2, 2)]
+    assert _grid_candidates((512, 512, 512), 6) == [(1, 6), (6, 1), (2, 3), (3, 2)]
+    assert _grid_candidates((512, 512, 512), 1) == [(1, 1)]
+    # y has 3 points: a grid dimension larger than 3 can never split it (X pencil: y over g1, Z pencil: y over g2)
+    assert _grid_candidates((64, 3, 100), 8) == []
+    assert _grid_candidates((64, 5, 100), 8) == [(2, 4), (4, 2)]
+    # x has 2 points: it is split over g1 in the Y and Z pencils
+    assert _grid_candidates((2, 64, 64), 8) == [(1, 8), (2, 4)]
+
+
+@pytest.mark.parametrize("dims,nranks", [((128, 64, 96), 8), ((48, 21, 36), 6), ((40, 33, 28), 4)])
+def test_grid_search_redecomposition_equals_cart_grid(dims, nranks):
+    """Switching a default plan to the grid 1 x g1 x g2 (what the grid search does between two
+    timings) gives, on every rank, exactly the pencils and exchange geometry of a plan CREATED on
+    that process grid."""
+    cfg = Config(enable_z_slab=False)
+    for g1, g2 in _grid_candidates(dims, nranks):
+        def switched(r, c):
+            p = PlanC2C(list(dims), comm=c, config=cfg, dry=True)
+            from dtfft_b200 import _lib
+            from dtfft_b200.plan import _check
+
+            _lib.lib().dtfftb_plan_dry_set_grid.restype = int
+            _check(_lib.lib().dtfftb_plan_dry_set_grid(p._h, g1, g2), "dtfftb_plan_dry_set_grid")
+            return p
+
+        a = dry_world(nranks, switched)
+        b = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True), cart_dims=[1, g1, g2])
+        for pa, pb in zip(a, b):
+            assert pa.grid_dims == pb.grid_dims == [1, g1, g2]
+            assert pa.local_sizes == pb.local_sizes and pa.alloc_bytes == pb.alloc_bytes
+            for lay in LAYOUT_OF_PENCIL:
+                ga, gb = pa.get_pencil(lay), pb.get_pencil(lay)
+                assert (ga.starts, ga.counts) == (gb.starts, gb.counts)
+            for t in (Transpose.X_TO_Y, Transpose.Y_TO_X, Transpose.Y_TO_Z, Transpose.Z_TO_Y):
+                da, db = pa.describe_exchange(t), pb.describe_exchange(t)
+                assert list(da["members"]) == list(db["members"])
+                assert np.array_equal(da["fused_boxes"], db["fused_boxes"])
+                for key in ("send_nd", "recv_nd", "send_counts", "send_displs", "recv_counts", "recv_displs"):
+                    assert np.array_equal(da[key], db[key]), key
+                assert (da["pack_kernel"], da["unpack_kernel"]) == (db["pack_kernel"], db["unpack_kernel"])
