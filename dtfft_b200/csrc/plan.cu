@@ -1480,7 +1480,9 @@ int Plan::execute_generic(void* in, void* out, bool fwd, void* aux, void* aux2) 
         RUN(run_fft(2, aux, out, -1));
     } else {
         auto zy = handles_.find(T_Z_TO_Y);
-        if (overlap_chunks_ > 1 && zy != handles_.end() && zy->second->can_chunk()) {
+        // (not for in-place calls: the last transform would become `in -> in`, which an out-of-place
+        // c2r plan cannot do; every rank calls alike, so the decision stays collective)
+        if (overlap_chunks_ > 1 && in != out && zy != handles_.end() && zy->second->can_chunk()) {
             // Stage overlap: the reference's choreography (below) transposes back INTO the buffer the
             // Z transform reads, which forbids storing chunk k while chunk k+1 is still being
             // transformed.  `in` is scratch on the backward pass anyway (the reference overwrites it
