@@ -174,7 +174,7 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
         if (rc) return rc;
         rc = k->set_peer_out(bases.data(), nullptr);
         if (rc) return rc;
-        if (fused_.size() > 16) fused_.clear();
+        if (fused_.size() >= kMaxCachedDestinations) forget_buffers();
         it = fused_.emplace(out, std::move(k)).first;
     }
     // channel: one pair per 1-D communicator id
@@ -227,7 +227,7 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
             rc = ks[(size_t)c]->set_peer_out(bases.data(), nullptr);
             if (rc) return rc;
         }
-        if (fused_chunks_.size() > 16) fused_chunks_.clear();
+        if (fused_chunks_.size() >= kMaxCachedDestinations) forget_buffers();
         it = fused_chunks_.emplace(key, std::move(ks)).first;
     }
     Kernel& kern = *it->second[(size_t)k];

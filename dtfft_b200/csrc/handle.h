@@ -56,7 +56,11 @@ public:
     void forget_buffers() {
         fused_.clear();
         fused_chunks_.clear();
+        ++evictions_;
     }
+    // Bumped whenever cached fused kernels are destroyed: a CUDA graph captured earlier may still
+    // point at their device tables and must not be replayed (Plan::execute compares the counters).
+    long long evictions() const { return evictions_; }
 
     // ---- stage overlap on the NVLINK_FUSED path (no reference counterpart) ----------------
     // The source pencil is cut along its SLOWEST axis into `nchunks` ranges; chunk k can be
@@ -88,6 +92,8 @@ private:
     std::vector<Box> fused_boxes_;  // per member, out_off relative to the member's `out`
     Family fused_family_ = FAM_NONE;
     std::map<const void*, std::unique_ptr<Kernel>> fused_;  // keyed by my `out` pointer
+    long long evictions_ = 0;
+    static constexpr size_t kMaxCachedDestinations = 256;
     Pencil send_;
     std::vector<Pencil> recv_by_member_;
     // chunk kernels keyed by (my `out` pointer, nchunks)

@@ -1310,6 +1310,11 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     }
     GraphEntry& g = it->second;
     if (g.failed) return execute_schedule(in, out, fwd, a1, a2, inplace);
+    if (g.exec && g.evictions != handle_evictions()) {  // kernels the graph points at were destroyed
+        cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+        return execute_schedule(in, out, fwd, a1, a2, inplace);  // eager: rebuilds them; next call re-captures
+    }
     if (!g.exec) {
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed);
@@ -1331,12 +1336,20 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
             return execute_schedule(in, out, fwd, a1, a2, inplace);
         }
         g.launches = stat_launches_, g.local = stat_local_, g.remote = stat_remote_, g.overlapped = stat_overlapped_;
+        g.evictions = handle_evictions();
     }
     stat_launches_ = g.launches, stat_local_ = g.local, stat_remote_ = g.remote, stat_overlapped_ = g.overlapped;
     cudaError_t ce = cudaGraphLaunch(g.exec, stream_);
     if (ce != cudaSuccess) return cuda_error(ce);
     ++stat_graph_replays_;
     return DTFFT_SUCCESS;
+}
+
+long long Plan::handle_evictions() const {
+    long long n = 0;
+    for (auto& kv : handles_) n += kv.second->evictions();
+    for (auto& kv : rhandles_) n += kv.second->evictions();
+    return n;
 }
 
 bool Plan::graphs_usable() const {

@@ -254,7 +254,9 @@ private:
         cudaGraphExec_t exec = nullptr;
         bool failed = false;
         int64_t launches = 0, local = 0, remote = 0, overlapped = 0;
+        long long evictions = 0;  // handle_evictions() when the graph was captured
     };
+    long long handle_evictions() const;
     std::map<GraphKey, GraphEntry> graphs_;
     bool graphs_enabled_ = true;
     int64_t stat_graph_replays_ = 0;
