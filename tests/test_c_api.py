@@ -45,6 +45,17 @@ def test_c_host_program():
     assert out.returncode == 0 and "api_host OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+def test_fastdiv_host_program():
+    """The work-item decoder's division by run-time constants is exact over its whole domain."""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "fastdiv_host")
+    out = subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(SRC, "fastdiv_host.cpp"), "-o", exe],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "bad 0" in out.stdout, out.stdout[-2000:]
+
+
 def test_cxx_wrapper_compiles():
     """include/dtfft_b200.hpp + the GPU program build warning-free with -Wall -Wextra -Werror."""
     assert os.path.exists(_build("api_gpu.cpp"))
