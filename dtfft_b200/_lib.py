@@ -128,6 +128,8 @@ def _declare_plan_api(L):
         "dtfftb_plan_create_dry": [C.c_int, C.c_int8, i32p, vp, vp, C.c_int, C.c_int, pvp],
         "dtfftb_plan_describe_exchange": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p,
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
+        "dtfftb_plan_describe_reshape": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
     }
     for name in ("alloc_size", "alloc_bytes", "element_size", "aux_size", "aux_bytes", "aux_size_transpose",
                  "aux_bytes_transpose", "aux_size_reshape", "aux_bytes_reshape"):

@@ -57,8 +57,10 @@ int NcclBackend::execute(void* in, void* out, cudaStream_t stream, void* aux) {
         ce = cudaMemcpyAsync(pout + self_rdispl_, pin + self_sdispl_, (size_t)self_bytes_, cudaMemcpyDeviceToDevice,
                              copy_stream_);
         if (ce != cudaSuccess) return cuda_error(ce);
-        rc = unpack_->execute(aux, out, copy_stream_, me_ + 1, false);
-        if (rc) return rc;
+        if (unpack_) {  // null = unpack-free reshape: the block is already in place
+            rc = unpack_->execute(aux, out, copy_stream_, me_ + 1, false);
+            if (rc) return rc;
+        }
     }
     // backend_nccl.F90:108-119
     ncclResult_t nr = ncclGroupStart();
@@ -79,7 +81,7 @@ int NcclBackend::execute(void* in, void* out, cudaStream_t stream, void* aux) {
     if (nr != ncclSuccess) return nccl_error(nr);
     if (pipelined_) {  // :126-132
         for (int i = 0; i < P_; ++i) {
-            if (rfloats_[i] > 0) {
+            if (rfloats_[i] > 0 && unpack_) {
                 rc = unpack_->execute(aux, out, stream, i + 1, false);
                 if (rc) return rc;
             }

@@ -381,4 +381,97 @@ RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankL
     return s;
 }
 
+namespace {
+// pack / unpack boxes and exchange tables of member `m`
+void reshape_tables(const std::vector<Pencil>& send_by_member, const std::vector<Pencil>& recv_by_member, int m,
+                    ReshapeGeometry* g) {
+    const int P = (int)send_by_member.size();
+    const RankLayout src = layout_of(send_by_member[(size_t)m]), dst = layout_of(recv_by_member[(size_t)m]);
+    g->pack_boxes.assign((size_t)P, Box{});
+    g->unpack_boxes.assign((size_t)P, Box{});
+    g->send_counts.clear(), g->send_displs.clear(), g->recv_counts.clear(), g->recv_displs.clear();
+    int64_t sdispl = 0, rdispl = 0;
+    for (int i = 0; i < P; ++i) {
+        bool tr = false;
+        const RankLayout peer_dst = layout_of(recv_by_member[(size_t)i]);
+        const RankLayout slot = slot_layout(src, peer_dst, peer_dst);
+        Box pb = intersect_box(src, slot, &tr);
+        pb.out_off += sdispl;
+        g->pack_boxes[(size_t)i] = pb;
+        const int64_t cnt = pb.empty() ? 0 : pb.volume();
+        g->send_counts.push_back(cnt), g->send_displs.push_back(sdispl);
+        sdispl += cnt;
+
+        const RankLayout peer_src = layout_of(send_by_member[(size_t)i]);
+        const RankLayout rslot = slot_layout(peer_src, dst, dst);
+        Box ub = intersect_box(rslot, dst, &tr);
+        ub.in_off += rdispl;
+        g->unpack_boxes[(size_t)i] = ub;
+        const int64_t rcnt = ub.empty() ? 0 : ub.volume();
+        g->recv_counts.push_back(rcnt), g->recv_displs.push_back(rdispl);
+        rdispl += rcnt;
+    }
+}
+
+// The box is a dense run that already sits where the exchange expects it.
+bool identity_placement(const Box& b) {
+    if (b.empty()) return true;
+    if (b.in_off != b.out_off || b.os0 != 1) return false;
+    if (b.n1 > 1 && (b.is1 != b.os1)) return false;
+    if (b.n2 > 1 && (b.is2 != b.os2)) return false;
+    return true;
+}
+}  // namespace
+
+ReshapeGeometry reshape_geometry(int rtype, const std::vector<Pencil>& send_by_member,
+                                 const std::vector<Pencil>& recv_by_member, int me) {
+    const int P = (int)send_by_member.size();
+    const int ndims = send_by_member[(size_t)me].ndims;
+    ReshapeGeometry g;
+    reshape_tables(send_by_member, recv_by_member, me, &g);
+    const bool to_pencils = rtype == R_X_BRICKS_TO_PENCILS || rtype == R_Z_BRICKS_TO_PENCILS;
+
+    // reshape_strat of `me` (:267-289)
+    if (ndims == 2) {
+        g.reshape_strat = 1;
+    } else {
+        bool zslab = true, yslab = true;
+        for (int i = 0; i < P; ++i) {
+            if (to_pencils) {
+                zslab = zslab && send_by_member[(size_t)me].counts[1] == recv_by_member[(size_t)i].counts[1];
+                yslab = yslab && send_by_member[(size_t)me].counts[2] == recv_by_member[(size_t)i].counts[2];
+            } else {
+                zslab = zslab && send_by_member[(size_t)i].counts[1] == recv_by_member[(size_t)me].counts[1];
+                yslab = yslab && send_by_member[(size_t)i].counts[2] == recv_by_member[(size_t)me].counts[2];
+            }
+        }
+        g.reshape_strat = zslab ? 1 : (yslab ? 2 : 3);
+    }
+
+    // is_pack_free / is_unpack_free: predicate of every member (:261-266, 479-484) + identity check
+    bool ref_all = true, pack_identity = true, unpack_identity = true;
+    for (int m = 0; m < P; ++m) {
+        bool ok = ndims == 2;
+        if (!ok) {
+            ok = true;
+            for (int i = 0; i < P; ++i)
+                ok = ok && send_by_member[(size_t)m].counts[1] == recv_by_member[(size_t)i].counts[1];
+        }
+        ref_all = ref_all && ok;
+        ReshapeGeometry gm;
+        const ReshapeGeometry* t = &g;
+        if (m != me) {
+            reshape_tables(send_by_member, recv_by_member, m, &gm);
+            t = &gm;
+        }
+        for (int i = 0; i < P; ++i) {
+            pack_identity = pack_identity && identity_placement(t->pack_boxes[(size_t)i]);
+            unpack_identity = unpack_identity && identity_placement(t->unpack_boxes[(size_t)i]);
+        }
+    }
+    g.is_pack_free = to_pencils && ref_all && pack_identity;
+    g.is_unpack_free = !to_pencils && ref_all && unpack_identity;
+    return g;
+}
+
 }  // namespace dtfftb

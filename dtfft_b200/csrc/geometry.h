@@ -35,6 +35,16 @@ struct Pencil {
     }
 };
 
+// One peer's box in ELEMENTS (a = input-contiguous axis).
+struct Box {
+    long long in_off = 0, out_off = 0;
+    long long n0 = 0, n1 = 1, n2 = 1;
+    long long is1 = 0, is2 = 0;
+    long long os0 = 1, os1 = 0, os2 = 0;
+    bool empty() const { return n0 <= 0 || n1 <= 0 || n2 <= 0; }
+    long long volume() const { return n0 * n1 * n2; }
+};
+
 void local_size(int n_global, int comm_dim, int comm_rank, int32_t* start, int32_t* count);
 // MPI_Dims_create for the shapes dtFFT asks for (zeros are free entries).
 void dims_create(int nnodes, int ndims, int32_t* dims);
@@ -101,7 +111,6 @@ struct RankLayout {
     }
 };
 RankLayout layout_of(const Pencil& p);
-struct Box;  // kernel_object.h
 // The part of `src` that lands in `dst`, as a strided box: element (global g) is read at
 // in_off + sum_j (g - src.start) * src.stride and written at out_off + ... of dst.
 // *transposing = the fastest axes differ (family T), else family R.
@@ -109,5 +118,25 @@ Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposin
 // Layout of the contiguous slot that carries the (src -> dst) block between two ranks:
 // the intersection, stored in the axis order of `order_like`.
 RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like);
+
+// ---- brick <-> pencil reshape over NCCL: pack -> all-to-all(v) -> unpack -------------------
+// Block (me -> i) is the global-index intersection of my source with i's destination, carried
+// in a contiguous slot in DESTINATION axis order (both sides of a reshape share the axis order,
+// so this is the reference's wire format: box (n1,n2,n3) packed densely, :343-376, 536-567).
+//   pack_boxes[i]   : my source -> slot i at send_displs[i]     (kernel `pack`)
+//   unpack_boxes[i] : slot i at recv_displs[i] -> my destination (kernel `unpack`)
+// is_pack_free / is_unpack_free restate src/dtfft_reshape_handle_generic.F90:261-266, 479-484:
+// the reference's predicate must hold on EVERY member (its allreduce) -- evaluated here from the
+// gathered layouts -- and, as a safety net the reference does not need, every member's boxes
+// must really be identity placements (block i already lies at its exchange displacement).
+// reshape_strat: 1 = z split, 2 = y split, 3 = 2-D split (:267-289).
+struct ReshapeGeometry {
+    std::vector<Box> pack_boxes, unpack_boxes;
+    std::vector<int64_t> send_counts, send_displs, recv_counts, recv_displs;  // elements
+    bool is_pack_free = false, is_unpack_free = false;
+    int reshape_strat = 0;
+};
+ReshapeGeometry reshape_geometry(int rtype, const std::vector<Pencil>& send_by_member,
+                                 const std::vector<Pencil>& recv_by_member, int me);
 
 }  // namespace dtfftb

@@ -2,6 +2,7 @@
 #include "handle.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "errors.h"
 
@@ -109,44 +110,43 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
         geo_.ttype = 0, geo_.rtype = rtype, geo_.ndims = ndims;
         geo_.comm_size = P, geo_.comm_rank = me, geo_.members = members;
         geo_.has_exchange = true, geo_.is_pipelined = pipelined;
-        geo_.pack_kernel = pipelined ? K_PACK_PIPELINED : K_PACK;
+        geo_.pack_kernel = K_PACK;  // :438
         geo_.unpack_kernel = pipelined ? K_UNPACK_PIPELINED : K_UNPACK;
         for (int j = 0; j < 3; ++j) geo_.send_dims[j] = j < ndims ? send.counts[j] : 1, geo_.recv_dims[j] = j < ndims ? recv.counts[j] : 1;
-        const RankLayout src = layout_of(send), dst = layout_of(recv);
-        std::vector<Box> pack_boxes((size_t)P), unpack_boxes((size_t)P);
-        int64_t sdispl = 0, rdispl = 0;
-        for (int i = 0; i < P; ++i) {
-            bool tr = false;
-            const RankLayout peer_dst = layout_of(recv_by_member[(size_t)i]);
-            RankLayout slot = slot_layout(src, peer_dst, peer_dst);
-            Box pb = intersect_box(src, slot, &tr);
-            pb.out_off += sdispl;
-            pack_boxes[(size_t)i] = pb;
-            const int64_t cnt = pb.empty() ? 0 : pb.volume();
-            geo_.send_counts.push_back(cnt), geo_.send_displs.push_back(sdispl);
-            sdispl += cnt;
-
-            const RankLayout peer_src = layout_of(send_by_member[(size_t)i]);
-            RankLayout rslot = slot_layout(peer_src, dst, dst);
-            Box ub = intersect_box(rslot, dst, &tr);
-            ub.in_off += rdispl;
-            unpack_boxes[(size_t)i] = ub;
-            const int64_t rcnt = ub.empty() ? 0 : ub.volume();
-            geo_.recv_counts.push_back(rcnt), geo_.recv_displs.push_back(rdispl);
-            rdispl += rcnt;
+        const ReshapeGeometry rg = reshape_geometry(rtype, send_by_member, recv_by_member, me);
+        geo_.send_counts = rg.send_counts, geo_.send_displs = rg.send_displs;
+        geo_.recv_counts = rg.recv_counts, geo_.recv_displs = rg.recv_displs;
+        geo_.reshape_strat = rg.reshape_strat;
+        // pack-free / unpack-free shortcuts (:261-266, 479-484); DTFFTB_RESHAPE_SHORTCUTS=0 keeps
+        // the three-step schedule (every rank must set it alike: aux sizes change with it)
+        const char* sc = getenv("DTFFTB_RESHAPE_SHORTCUTS");
+        const bool shortcuts = !(sc && sc[0] == '0');
+        geo_.is_pack_free = shortcuts && rg.is_pack_free;
+        geo_.is_unpack_free = shortcuts && rg.is_unpack_free;
+        if (geo_.is_pack_free) {
+            geo_.pack_kernel = K_DUMMY;
+            pack_.reset();
+        } else {
+            rc = pack_->create_boxes(FAM_R, es_, rg.pack_boxes);
+            if (rc) return rc;
         }
-        rc = pack_->create_boxes(FAM_R, es_, pack_boxes);
-        if (rc) return rc;
-        rc = unpack_->create_boxes(FAM_R, es_, unpack_boxes);
-        if (rc) return rc;
+        if (geo_.is_unpack_free) {  // :623
+            geo_.unpack_kernel = K_DUMMY;
+            unpack_.reset();
+        } else {
+            rc = unpack_->create_boxes(FAM_R, es_, rg.unpack_boxes);
+            if (rc) return rc;
+        }
     }
     std::vector<int> mapping = members;  // NCCL communicator spans the world: member -> world rank
     rc = nccl_->create(backend_, ctx_.nccl, me, mapping, geo_.send_displs, geo_.send_counts, geo_.recv_displs,
                        geo_.recv_counts, es_);
     if (rc) return rc;
-    if (pipelined) nccl_->set_unpack_kernel(unpack_.get());
+    if (pipelined) nccl_->set_unpack_kernel(unpack_.get());  // null when unpack-free: nothing to run
     aux_bytes_ = nccl_->aux_bytes();
-    launches_ = pipelined ? 1 + P : 2;
+    if (geo_.is_pack_free || geo_.is_unpack_free)  // :684-686
+        aux_bytes_ = std::max<int64_t>(aux_bytes_, es_ * std::max(send_elems_, recv_elems_));
+    launches_ = (pack_ ? 1 : 0) + (unpack_ ? (pipelined ? P : 1) : 0);
     created_ = true;
     return DTFFT_SUCCESS;
 }
@@ -243,11 +243,27 @@ int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) 
     if (!has_exchange_) return pack_->execute(in, out, stream, 0, false);
     if (backend_ == BACKEND_NVLINK_FUSED) return execute_fused(in, out, stream);
     int rc;
-    if (nccl_->is_pipelined()) {  // reshape_handle_generic.F90:723-730
+    if (nccl_->is_pipelined()) {
         if (!aux) return DTFFT_ERROR_INVALID_AUX;
+        if (geo_.is_pack_free)  // :711-716  in -> aux exchange, aux -> out unpack
+            return nccl_->execute(in, out, stream, aux);
         rc = pack_->execute_all(in, aux, stream);  // in -> aux   pack
         if (rc) return rc;
-        return nccl_->execute(aux, out, stream, in);  // aux -> in exchange, in -> out unpack
+        if (geo_.is_unpack_free)  // :717-722  aux -> out exchange (received straight into `out`)
+            return nccl_->execute(aux, in, stream, out);
+        return nccl_->execute(aux, out, stream, in);  // :723-730  aux -> in exchange, in -> out unpack
+    }
+    if (geo_.is_pack_free) {  // :734-740  in -> aux exchange, aux -> out unpack
+        if (!aux) return DTFFT_ERROR_INVALID_AUX;
+        rc = nccl_->execute(in, aux, stream, aux);
+        if (rc) return rc;
+        return unpack_->execute_all(aux, out, stream);
+    }
+    if (geo_.is_unpack_free) {  // :742-746  in -> aux pack, aux -> out exchange
+        if (!aux) return DTFFT_ERROR_INVALID_AUX;
+        rc = pack_->execute_all(in, aux, stream);
+        if (rc) return rc;
+        return nccl_->execute(aux, out, stream, aux);
     }
     rc = pack_->execute_all(in, out, stream);  // :752  in -> out  pack
     if (rc) return rc;

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "blocks.h"
+#include "geometry.h"  // Box
 #include "kernels.cuh"
 
 namespace dtfftb {
@@ -35,16 +36,6 @@ enum KernelType : int {
 };
 
 enum Family : int { FAM_NONE = 0, FAM_COPY = 1, FAM_T = 2, FAM_R = 3 };
-
-// One peer's box in ELEMENTS (a = input-contiguous axis).
-struct Box {
-    long long in_off = 0, out_off = 0;
-    long long n0 = 0, n1 = 1, n2 = 1;
-    long long is1 = 0, is2 = 0;
-    long long os0 = 1, os1 = 0, os2 = 0;
-    bool empty() const { return n0 <= 0 || n1 <= 0 || n2 <= 0; }
-    long long volume() const { return n0 * n1 * n2; }
-};
 
 bool is_per_neighbor_kind(int t);
 bool needs_neighbor_data(int t);

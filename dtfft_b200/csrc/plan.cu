@@ -618,18 +618,22 @@ int Plan::handle_spec(int type, HandleSpec* hs) const {
         const bool x_side = type == R_X_BRICKS_TO_PENCILS || type == R_X_PENCILS_TO_BRICKS;
         const bool to_pencils = type == R_X_BRICKS_TO_PENCILS || type == R_Z_BRICKS_TO_PENCILS;
         const int last = nd - 1, csize = brick_grid_[last];
-        std::vector<std::pair<int, int>> keyed;
+        std::vector<std::pair<std::pair<long long, int>, int>> keyed;
         for (int r = 0; r < P; ++r) {
             bool same = true;
-            if (x_side) {  // bricks sharing their (y, z) footprint = one line of the brick grid along x
+            if (x_side) {  // bricks sharing their (y, z) footprint = one line of the brick grid along x,
+                           // ranked by where their X pencil starts (MPI_Comm_split key, reshape_plan.F90:162-167)
                 for (int d = 1; d < nd; ++d)
                     if (brick_coords_[(size_t)r][(size_t)d] != brick_coords_[(size_t)me][(size_t)d]) same = false;
-                if (same) keyed.push_back({brick_coords_[(size_t)r][0], r});
+                const Pencil& xp = pencils_[(size_t)r][0];
+                long long key = xp.starts[1];
+                if (nd == 3) key += (long long)xp.starts[2] * xp.counts[1] * brick_grid_[1];
+                if (same) keyed.push_back({{key, brick_coords_[(size_t)r][0]}, r});
             } else {  // the `c` consecutive ranks of the last grid dimension that pool their data
                 for (int d = 1; d < nd; ++d)
                     if (d != last && coords_[(size_t)r][(size_t)d] != coords_[(size_t)me][(size_t)d]) same = false;
                 if (same && coords_[(size_t)r][(size_t)last] / csize == coords_[(size_t)me][(size_t)last] / csize)
-                    keyed.push_back({coords_[(size_t)r][(size_t)last], r});
+                    keyed.push_back({{coords_[(size_t)r][(size_t)last], 0}, r});
             }
         }
         std::sort(keyed.begin(), keyed.end());
@@ -713,6 +717,17 @@ int Plan::describe_exchange(int type, ExchangeDescription* d) const {
         d->fused[(size_t)i] = intersect_box(src, layout_of(hs.recv[(size_t)i]), &tr);
         if (!d->fused[(size_t)i].empty() && tr) d->fused_transposing = true;
     }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::describe_reshape(int rtype, std::vector<int>* members, int* me, ReshapeGeometry* g) const {
+    HandleSpec hs;
+    if (std::abs(rtype) <= 3) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
+    int rc = handle_spec(rtype, &hs);
+    if (rc) return rc;
+    if (members) *members = hs.members;
+    if (me) *me = hs.me;
+    *g = reshape_geometry(rtype, hs.send, hs.recv, hs.me);
     return DTFFT_SUCCESS;
 }
 
@@ -993,6 +1008,24 @@ size_t Plan::aux_bytes_transpose() const {
 
 size_t Plan::aux_bytes_reshape() const {
     size_t a = 0;
+    if (dry_ && is_reshape_enabled_ && (reshape_backend_ == BACKEND_NCCL || reshape_backend_ == BACKEND_NCCL_PIPELINED)) {
+        // what the handles would report: pipelined workspace (abstract_backend.F90:196-201) and the
+        // pack-free / unpack-free staging buffer (reshape_handle_generic.F90:684-686)
+        const char* sc = getenv("DTFFTB_RESHAPE_SHORTCUTS");
+        const bool shortcuts = !(sc && sc[0] == '0');
+        for (int t = R_X_BRICKS_TO_PENCILS; t <= R_Z_BRICKS_TO_PENCILS; ++t) {
+            HandleSpec hs;
+            if (handle_spec(t, &hs) || hs.members.size() < 2) continue;
+            const ReshapeGeometry g = reshape_geometry(t, hs.send, hs.recv, hs.me);
+            long long s = 0, r = 0;
+            for (auto c : g.send_counts) s += c;
+            for (auto c : g.recv_counts) r += c;
+            if (backend_is_pipelined(reshape_backend_)) a = std::max(a, (size_t)(std::max(s, r) * hs.es));
+            if (shortcuts && (g.is_pack_free || g.is_unpack_free))
+                a = std::max(a, (size_t)(std::max(hs.send[(size_t)hs.me].size(), hs.recv[(size_t)hs.me].size()) * hs.es));
+        }
+        return a;
+    }
     for (auto& kv : rhandles_) a = std::max(a, (size_t)kv.second->aux_bytes());
     return a;
 }

@@ -149,6 +149,9 @@ public:
         bool fused_transposing = false;
     };
     int describe_exchange(int type, ExchangeDescription* d) const;
+    // Brick <-> pencil reshape over the NCCL backends: pack / unpack boxes, exchange tables and
+    // the pack-free / unpack-free flags (geometry.h: reshape_geometry).
+    int describe_reshape(int rtype, std::vector<int>* members, int* me, ReshapeGeometry* g) const;
     std::vector<int> transpose_types() const;
 
 private:

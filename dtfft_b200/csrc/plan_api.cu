@@ -561,6 +561,39 @@ dtfft_error_t dtfftb_plan_describe_exchange(dtfft_plan_t plan, int type, int32_t
     return DTFFT_SUCCESS;
 }
 
+dtfft_error_t dtfftb_plan_describe_reshape(dtfft_plan_t plan, int reshape_type, int32_t cap, int32_t* n_members,
+                                           int32_t* my_index, int32_t* members, int64_t* pack_boxes,
+                                           int64_t* unpack_boxes, int64_t* counts_displs, int32_t* flags) {
+    PLAN_OR_RETURN(plan);
+    if (!n_members) return DTFFT_ERROR_INVALID_USAGE;
+    std::vector<int> mem;
+    int me = 0;
+    dtfftb::ReshapeGeometry g;
+    int rc = P(plan)->describe_reshape(reshape_type, &mem, &me, &g);
+    if (rc) return E(rc);
+    const int np = (int)mem.size();
+    *n_members = np;
+    if (my_index) *my_index = me;
+    if (flags) flags[0] = g.is_pack_free ? 1 : 0, flags[1] = g.is_unpack_free ? 1 : 0, flags[2] = g.reshape_strat;
+    if (np > cap) return DTFFT_SUCCESS;  // caller re-queries with a larger capacity
+    auto put = [](int64_t* o, const dtfftb::Box& b) {
+        o[0] = b.empty() ? 0 : b.n0, o[1] = b.n1, o[2] = b.n2, o[3] = b.in_off, o[4] = b.out_off;
+        o[5] = b.is1, o[6] = b.is2, o[7] = b.os0, o[8] = b.os1, o[9] = b.os2;
+    };
+    for (int i = 0; i < np; ++i) {
+        if (members) members[i] = mem[(size_t)i];
+        if (pack_boxes) put(pack_boxes + 10 * i, g.pack_boxes[(size_t)i]);
+        if (unpack_boxes) put(unpack_boxes + 10 * i, g.unpack_boxes[(size_t)i]);
+        if (counts_displs) {
+            counts_displs[0 * np + i] = g.send_counts[(size_t)i];
+            counts_displs[1 * np + i] = g.send_displs[(size_t)i];
+            counts_displs[2 * np + i] = g.recv_counts[(size_t)i];
+            counts_displs[3 * np + i] = g.recv_displs[(size_t)i];
+        }
+    }
+    return DTFFT_SUCCESS;
+}
+
 int dtfftb_plan_peer_error(dtfft_plan_t plan) {
     if (!plan) return 0;
     return P(plan)->peer_error();

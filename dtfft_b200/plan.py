@@ -444,6 +444,26 @@ class Plan:
                 "send_displs": cd[1], "recv_counts": cd[2], "recv_displs": cd[3], "fused_boxes": boxes,
                 "fused_transposing": bool(tr.value)}
 
+    def describe_reshape(self, type_) -> dict:
+        """NCCL-path geometry of one brick <-> pencil reshape on this rank (dtfftb_plan_describe_reshape)."""
+        import numpy as np
+
+        L = _lib.lib()
+        n, me = C.c_int32(0), C.c_int32(0)
+        _check(L.dtfftb_plan_describe_reshape(self._h, int(type_), 0, C.byref(n), C.byref(me), None, None, None, None,
+                                              None), "dtfftb_plan_describe_reshape")
+        P = n.value
+        members, flags = np.zeros(P, np.int32), np.zeros(3, np.int32)
+        pack, unpack = np.zeros((P, 10), np.int64), np.zeros((P, 10), np.int64)
+        cd = np.zeros((4, P), np.int64)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        _check(L.dtfftb_plan_describe_reshape(self._h, int(type_), P, C.byref(n), C.byref(me), ip(members), lp(pack),
+                                              lp(unpack), lp(cd), ip(flags)), "dtfftb_plan_describe_reshape")
+        return {"members": members.tolist(), "me": me.value, "pack_boxes": pack, "unpack_boxes": unpack,
+                "send_counts": cd[0], "send_displs": cd[1], "recv_counts": cd[2], "recv_displs": cd[3],
+                "is_pack_free": bool(flags[0]), "is_unpack_free": bool(flags[1]), "reshape_strat": int(flags[2])}
+
     def peer_error(self) -> int:
         return int(_lib.lib().dtfftb_plan_peer_error(self._h))
 

@@ -345,6 +345,16 @@ dtfft_error_t dtfftb_plan_describe_exchange(dtfft_plan_t plan, int type, int32_t
                                             int32_t* my_index, int32_t* members, int32_t* kernels, int32_t* send_nd,
                                             int32_t* recv_nd, int64_t* counts_displs, int64_t* fused_boxes,
                                             int32_t* fused_transposing);
+/* Brick <-> pencil reshape `reshape_type` over the NCCL backends on this rank (dry and real plans):
+ * the pack -> all-to-all(v) -> unpack geometry of reshape_handle_generic for reshapes
+ * (src/dtfft_reshape_handle_generic.F90:343-376, 536-567) derived from global-index intersections.
+ *   pack_boxes    10 x P int64 (layout as fused_boxes): my source -> slot p at send displ p
+ *   unpack_boxes  10 x P int64: slot p at recv displ p -> my destination
+ *   counts_displs 4 x P int64: send counts, send displs, recv counts, recv displs (elements)
+ *   flags[3]      is_pack_free, is_unpack_free (:261-266, 479-484), reshape_strat (:267-289) */
+dtfft_error_t dtfftb_plan_describe_reshape(dtfft_plan_t plan, int reshape_type, int32_t cap, int32_t* n_members,
+                                           int32_t* my_index, int32_t* members, int64_t* pack_boxes,
+                                           int64_t* unpack_boxes, int64_t* counts_displs, int32_t* flags);
 
 #ifdef __cplusplus
 }

@@ -418,3 +418,152 @@ def z_bricks(dims, comm_dims, coords, last_pencils, brick_grid):
         else:
             out.append(Pencil(2, [s0, lo], [c0, cnt]))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Brick <-> pencil reshapes: neighbor_data, strategies, pack-free / unpack-free
+# --------------------------------------------------------------------------------------
+X_BRICKS_TO_PENCILS, X_PENCILS_TO_BRICKS, Z_PENCILS_TO_BRICKS, Z_BRICKS_TO_PENCILS = 11, 12, 13, 14
+
+
+@dataclass
+class ReshapeGeometry(HandleGeometry):
+    is_pack_free: bool = False
+    is_unpack_free: bool = False
+    reshape_strat: int = 0
+
+
+def reshape_geometry(rtype: int, send_by_member, recv_by_member, me: int, members,
+                     pipelined: bool = False) -> ReshapeGeometry:
+    """What ``reshape_handle_generic%create`` derives for a brick <-> pencil reshape
+    (src/dtfft_reshape_handle_generic.F90): send boxes :343-376, send-side displacements by
+    strategy :380-404, recv boxes :536-567, recv-side displacements :590-611, strategy :267-289,
+    ``is_pack_free`` :261-266, ``is_unpack_free`` :479-484 (both are all-reduced over the
+    communicator: every member's predicate must hold), kernel kinds :425-447, 618-624.
+    Both sides of a reshape store their axes in the same order, so the formulas work on local
+    axes 1..3 whatever the global axes are (X bricks / X pencils: x,y,z; Z bricks / Z pencils: z,x,y)."""
+    p = len(members)
+    send, recv = send_by_member[me], recv_by_member[me]
+    ndims = len(send.counts)
+    to_pencils = rtype in (X_BRICKS_TO_PENCILS, Z_BRICKS_TO_PENCILS)
+    geo = ReshapeGeometry(0, p, me, list(members), list(send.counts), list(recv.counts), K.KERNEL_COPY, None)
+    if p == 1:                                                                       # :246-253
+        return geo
+    S = lambda d, r: send_by_member[r].counts[d - 1]
+    s = lambda d, r: send_by_member[r].starts[d - 1]
+    D = lambda d, r: recv_by_member[r].counts[d - 1]
+    d_ = lambda d, r: recv_by_member[r].starts[d - 1]
+    dims_of = range(1, ndims + 1)
+
+    def pack_free_of(m):                                                             # :261-262, 479-480
+        return ndims == 2 or all(S(2, m) == D(2, i) for i in range(p))
+
+    geo.is_pack_free = to_pencils and all(pack_free_of(m) for m in range(p))         # :264-266
+    geo.is_unpack_free = (not to_pencils) and all(pack_free_of(m) for m in range(p))  # :481-484
+    if ndims == 2:                                                                   # :289
+        strat = 1
+    else:                                                                            # :267-288
+        if to_pencils:
+            zslab = all(S(2, me) == D(2, i) for i in range(p))
+            yslab = all(S(3, me) == D(3, i) for i in range(p))
+        else:
+            zslab = all(S(2, i) == D(2, me) for i in range(p))
+            yslab = all(S(3, i) == D(3, me) for i in range(p))
+        strat = 1 if zslab else (2 if yslab else 3)
+    geo.reshape_strat = strat
+
+    def send_box(i, frm):                                                            # :343-376
+        if to_pencils:
+            ln = [S(1, frm)] + [D(d, i) for d in dims_of if d > 1]
+            ls = [s(1, frm)] + [d_(d, i) for d in dims_of if d > 1]
+        else:
+            ln = [D(1, i)] + [S(d, frm) for d in dims_of if d > 1]
+            ls = [d_(1, i)] + [s(d, frm) for d in dims_of if d > 1]
+        return ln, ls
+
+    send_nd = np.zeros((p, 5), dtype=np.int32)
+    sdispl = ssdispl = 0
+    for i in range(p):
+        ln, ls = send_box(i, me)
+        if to_pencils:                                                               # :380-391
+            if strat == 1:
+                send_nd[i, 3] = ssdispl
+                ssdispl += int(np.prod(ln))
+            elif strat == 2:
+                send_nd[i, 3] = ssdispl
+                ssdispl += ln[0] * ln[1]
+            else:
+                ssdispl = (d_(3, i) - s(3, me)) * S(1, me) * S(2, me) + (d_(2, i) - s(2, me)) * S(1, me)
+                send_nd[i, 3] = ssdispl
+        else:                                                                        # :402
+            send_nd[i, 3] = ls[0]
+        send_nd[i, 0], send_nd[i, 1] = ln[0], ln[1]
+        send_nd[i, 2] = ln[2] if ndims == 3 else 1
+        send_nd[i, 4] = sdispl                                                       # :413
+        cnt = int(np.prod(ln))
+        geo.send_counts.append(cnt)
+        geo.send_displs.append(sdispl)
+        sdispl += cnt
+
+    recv_nd = np.zeros((p, 5), dtype=np.int32)
+    rdispl = rrdispl = 0
+    for i in range(p):
+        ln_i, _ = send_box(me, i)                                                    # :421-422, 488-489
+        recvsize = int(np.prod(ln_i))
+        ln, ls = [0] * ndims, [0] * ndims
+        if recvsize > 0:                                                             # :536-567
+            if to_pencils:
+                ln = [S(1, i)] + [D(d, me) for d in dims_of if d > 1]
+                ls = [s(1, i)] + [d_(d, me) for d in dims_of if d > 1]
+            else:
+                ln = [D(1, me)] + [S(d, i) for d in dims_of if d > 1]
+                ls = [d_(1, me)] + [s(d, i) for d in dims_of if d > 1]
+        recv_nd[i, 0], recv_nd[i, 1] = ln[0], ln[1]
+        recv_nd[i, 2] = ln[2] if ndims == 3 else 1
+        recv_nd[i, 3] = rdispl                                                       # :582
+        if to_pencils:                                                               # :590-591
+            recv_nd[i, 4] = ls[0]
+        elif strat in (1, 2):                                                        # :594-597
+            recv_nd[i, 4] = rrdispl
+            rrdispl += ln[0] * ln[1]
+        else:                                                                        # :598-600
+            rrdispl = (abs(d_(3, me) - s(3, i)) * D(1, me) * D(2, me) + abs(d_(2, me) - s(2, i)) * D(1, me)) \
+                if ndims == 3 else 0
+            recv_nd[i, 4] = rrdispl
+        geo.recv_counts.append(recvsize)
+        geo.recv_displs.append(rdispl)
+        rdispl += recvsize
+
+    geo.is_pipelined = pipelined
+    geo.pack_kernel = K.KERNEL_PACK                                                  # :437-441 (non-fused backends)
+    if geo.is_pack_free:                                                             # :442
+        geo.pack_kernel = K.KERNEL_DUMMY
+    geo.unpack_kernel = K.KERNEL_UNPACK_PIPELINED if pipelined else K.KERNEL_UNPACK  # :618-619
+    if geo.is_unpack_free:                                                           # :623
+        geo.unpack_kernel = K.KERNEL_DUMMY
+    geo.send_nd, geo.recv_nd = send_nd, recv_nd
+    return geo
+
+
+def reshape_members(rank: int, rtype: int, brick_grid, brick_coords, coords, x_pencils):
+    """Global ranks of the 1-D communicator of a reshape, in communicator order
+    (src/dtfft_reshape_plan.F90:160-171).  X side: the bricks of one x-line of the brick grid
+    (``ipencil%comms(1)``), re-ranked by where their X pencil starts -- ``MPI_Comm_split`` key
+    ``starts(2) + starts(3) * counts(2) * init_grid(2)``, ties by the old rank (= x coordinate).
+    Z side: ``NEIGHBOR_GROUP`` of ``c`` consecutive ranks of the last grid dimension, c = size of
+    the brick grid along the last axis (``create_custom_comm``)."""
+    P, nd = len(coords), len(coords[0])
+    last = nd - 1
+    if rtype in (X_BRICKS_TO_PENCILS, X_PENCILS_TO_BRICKS):
+        def key(q):
+            xp = x_pencils[q]
+            k = xp.starts[1]
+            if nd == 3:
+                k += xp.starts[2] * xp.counts[1] * brick_grid[1]
+            return (k, brick_coords[q][0])
+        line = [q for q in range(P) if all(brick_coords[q][d] == brick_coords[rank][d] for d in range(1, nd))]
+        return sorted(line, key=key)
+    csize = brick_grid[last]
+    grp = [q for q in range(P) if coords[q][last] // csize == coords[rank][last] // csize
+           and all(coords[q][d] == coords[rank][d] for d in range(1, nd) if d != last)]
+    return sorted(grp, key=lambda q: coords[q][last])

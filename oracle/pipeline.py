@@ -141,3 +141,81 @@ def apply_boxes(src, dsts, boxes, members):
         iidx = (ioff + a + bb * is1 + c * is2).ravel()
         oidx = (ooff + a * os0 + bb * os1 + c * os2).ravel()
         dsts[members[i]][oidx] = src[iidx]
+
+
+def _exchange(geos, send_bufs, recv_bufs):
+    """all-to-all(v) on simulated ranks: member i of my communicator sends me
+    ``send_counts`` elements from its ``send_displs`` into my ``recv_displs``
+    (src/dtfft_backend_nccl.F90:108-119, element units here)."""
+    for r, g in enumerate(geos):
+        for i, peer in enumerate(g.members):
+            gp = geos[peer]
+            j = gp.members.index(r)
+            cnt = g.recv_counts[i]
+            assert cnt == gp.send_counts[j], (r, peer)
+            so, ro = gp.send_displs[j], g.recv_displs[i]
+            recv_bufs[r][ro: ro + cnt] = send_bufs[peer][so: so + cnt]
+
+
+def reshape_generic(inputs, geos, out_sizes, buf_sizes, execute=K.execute):
+    """The reference's reshape schedule (src/dtfft_reshape_handle_generic.F90:695-759) for a brick
+    <-> pencil reshape on simulated ranks, including the pack-free (:711-716, 734-740) and
+    unpack-free (:717-722, 742-746) shortcuts.  ``geos[r]`` = :func:`oracle.layout.reshape_geometry`
+    of global rank r, ``inputs[r]`` its source array (flat), ``buf_sizes[r]`` the plan's alloc size.
+    Returns the destination arrays trimmed to ``out_sizes[r]``."""
+    n = len(geos)
+    dtype = inputs[0].dtype
+    a = [np.zeros(buf_sizes[r], dtype) for r in range(n)]        # "in"
+    b = [np.full(buf_sizes[r], -7, dtype) for r in range(n)]     # "out"
+    w = [np.full(buf_sizes[r], -9, dtype) for r in range(n)]     # "aux" (kwargs%p1)
+    for r in range(n):
+        a[r][: inputs[r].size] = inputs[r]
+    if geos[0].comm_size == 1:
+        return [a[r][: out_sizes[r]].copy() for r in range(n)]
+
+    def run(kernel, dims, src, dst, nd):
+        if kernel == K.KERNEL_DUMMY:
+            return
+        if kernel in K.PER_NEIGHBOR_KERNELS:
+            for i in range(nd.shape[0]):
+                execute(kernel, dims, src, dst, nd, i + 1)
+        else:
+            execute(kernel, dims, src, dst, nd)
+
+    g0 = geos[0]
+    if g0.is_pipelined:
+        if g0.is_pack_free:        # in -> aux exchange, aux -> out unpack
+            _exchange(geos, a, w)
+            for r, g in enumerate(geos):
+                run(g.unpack_kernel, g.recv_dims, w[r], b[r], g.recv_nd)
+        elif g0.is_unpack_free:    # in -> aux pack, aux -> out exchange
+            for r, g in enumerate(geos):
+                run(g.pack_kernel, g.send_dims, a[r], w[r], g.send_nd)
+            _exchange(geos, w, b)
+        else:                      # in -> aux pack, aux -> in exchange, in -> out unpack
+            for r, g in enumerate(geos):
+                run(g.pack_kernel, g.send_dims, a[r], w[r], g.send_nd)
+            _exchange(geos, w, a)
+            for r, g in enumerate(geos):
+                run(g.unpack_kernel, g.recv_dims, a[r], b[r], g.recv_nd)
+    elif g0.is_pack_free:          # in -> aux exchange, aux -> out unpack
+        _exchange(geos, a, w)
+        for r, g in enumerate(geos):
+            run(g.unpack_kernel, g.recv_dims, w[r], b[r], g.recv_nd)
+    elif g0.is_unpack_free:        # in -> aux pack, aux -> out exchange
+        for r, g in enumerate(geos):
+            run(g.pack_kernel, g.send_dims, a[r], w[r], g.send_nd)
+        _exchange(geos, w, b)
+    else:                          # in -> out pack, out -> in exchange, in -> out unpack
+        for r, g in enumerate(geos):
+            run(g.pack_kernel, g.send_dims, a[r], b[r], g.send_nd)
+        _exchange(geos, b, a)
+        for r, g in enumerate(geos):
+            run(g.unpack_kernel, g.recv_dims, a[r], b[r], g.recv_nd)
+    return [b[r][: out_sizes[r]] for r in range(n)]
+
+
+def apply_local_boxes(src, dst, boxes):
+    """Emulate one all-peer launch of the product's pack / unpack kernel over explicit boxes
+    (dtfftb_plan_describe_reshape): box = (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2)."""
+    apply_boxes(src, [dst] * len(boxes), boxes, list(range(len(boxes))))

@@ -147,7 +147,13 @@ def main():
                 checked += 1
 
         # bricks -> pencils -> bricks with uneven cuts (needs an even number of ranks)
-        if world % 2 == 0:
+        # NCCL backends: once with the reference's pack-free / unpack-free shortcuts
+        # (reshape_handle_generic.F90:711-746; the Z reshapes always take them, the X reshapes when
+        # the bricks are split along z) and once with the plain three-step schedule
+        for shortcuts in (("1", "0") if backend != Backend.NVLINK_FUSED and world % 2 == 0 else ("1",)):
+            if world % 2:
+                break
+            os.environ["DTFFTB_RESHAPE_SHORTCUTS"] = shortcuts
             # brick grid 2 x ny x nz; with nz = 2 the Z bricks differ from the Z pencils
             nz = 2 if world % 4 == 0 else 1
             ny = world // (2 * nz)
@@ -162,6 +168,9 @@ def main():
                                       [int(cuts[0][i]), int(cuts[1][j]), int(cuts[2][k])]))
             cfg = Config(backend=backend, reshape_backend=backend, enable_z_slab=False, enable_fourier_reshape=True)
             plan = PlanR2R(Pencil(*boxes[rank]), comm=comm, config=cfg)
+            if world == 2:  # z = 70 > 32 * 2: z split, so the X reshapes are pack-free / unpack-free
+                flags = [plan.describe_reshape(t) for t in (Reshape.X_BRICKS_TO_PENCILS, Reshape.X_PENCILS_TO_BRICKS)]
+                assert flags[0]["is_pack_free"] and flags[1]["is_unpack_free"]
             dims = plan.dims
             G = P.global_array(dims, np.float64, kind="index")
             b1 = oracle_pencil(plan.get_pencil(Layout.X_BRICKS))
@@ -201,6 +210,7 @@ def main():
                 plan.mem_free(b_)
             plan.destroy()
             checked += 1
+        os.environ.pop("DTFFTB_RESHAPE_SHORTCUTS", None)
 
     # DTFFT_PATIENT: timed backend choice (run_autotune_backend), then a correct transposition
     plan = PlanC2C([128, 64, 96], comm=comm, effort=Effort.PATIENT, config=Config(enable_z_slab=False))
