@@ -397,15 +397,18 @@ int Plan::choose_decomposition(const dtfft_pencil_t* pencil) {
     std::vector<std::array<int32_t, 3>> bcoord((size_t)P, {0, 0, 0});
     for (int r = 0; r < P; ++r)
         for (int d = 0; d < nd; ++d) {
-            std::vector<int32_t> line;
+            // a rank with no points along d may share its start with a neighbour (:1066-1068);
+            // ties keep rank order (stable insertion sort, :1005-1031)
+            std::vector<std::pair<int32_t, int>> line;
             for (int i = 0; i < P; ++i) {
                 bool same = true;
                 for (int j = 0; j < nd; ++j)
                     if (j != d && (up[i].starts[j] != up[r].starts[j] || up[i].counts[j] != up[r].counts[j])) same = false;
-                if (same && (i == r || up[i].starts[d] != up[r].starts[d])) line.push_back(up[i].starts[d]);
+                const bool tie_with_empty = up[i].starts[d] == up[r].starts[d] && (up[i].counts[d] == 0 || up[r].counts[d] == 0);
+                if (i == r || (same && (up[i].starts[d] != up[r].starts[d] || tie_with_empty))) line.push_back({up[i].starts[d], i});
             }
             std::sort(line.begin(), line.end());
-            int idx = (int)(std::lower_bound(line.begin(), line.end(), up[r].starts[d]) - line.begin());
+            int idx = (int)(std::lower_bound(line.begin(), line.end(), std::make_pair(up[r].starts[d], r)) - line.begin());
             bcoord[(size_t)r][(size_t)d] = idx;
             if (r == me) bgrid[d] = (int32_t)line.size();
         }

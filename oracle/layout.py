@@ -314,11 +314,13 @@ def grid_from_boxes(starts, counts):
     grid = [1] * nd
     for r in range(P):
         for d in range(nd):
-            line = sorted(starts[i][d] for i in range(P)
-                          if all(starts[i][j] == starts[r][j] and counts[i][j] == counts[r][j]
-                                 for j in range(nd) if j != d)
-                          and (i == r or starts[i][d] != starts[r][d]))
-            coords[r][d] = line.index(starts[r][d])
+            line = sorted((starts[i][d], i) for i in range(P)
+                          if i == r or (all(starts[i][j] == starts[r][j] and counts[i][j] == counts[r][j]
+                                            for j in range(nd) if j != d)
+                                        and (starts[i][d] != starts[r][d]
+                                             # a rank without points along d may share its start (:1066-1068)
+                                             or counts[i][d] == 0 or counts[r][d] == 0)))
+            coords[r][d] = line.index((starts[r][d], r))
             if r == 0:
                 grid[d] = len(line)
     return grid, coords

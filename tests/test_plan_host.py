@@ -180,6 +180,45 @@ def test_user_pencils(dims, grid):
     Config()._commit()
 
 
+def test_user_pencils_with_an_empty_rank():
+    """A rank without points along a split axis (more ranks than points: dtFFT's own get_local_size
+    gives rank 0 nothing for 3 points on 4 ranks) joins the 1-D communicator of the neighbour it
+    shares its start with (create_1d_comm, src/dtfft_pencil.F90:1066-1068); its kernels are no-ops
+    (abstract_kernel.F90:236-240) and every transposition still reproduces the datatype path."""
+    dims = (16, 3, 8)
+    boxes = [([0, 0, 0], [16, 0, 8]), ([0, 0, 0], [16, 1, 8]), ([0, 1, 0], [16, 1, 8]), ([0, 2, 0], [16, 1, 8])]
+    n = len(boxes)
+    cfg = Config(enable_z_slab=False)
+    plans = dry_world(n, lambda r, c: PlanC2C(Pencil(*boxes[r]), comm=c, config=cfg, dry=True))
+    starts, counts = [b[0] for b in boxes], [b[1] for b in boxes]
+    ggrid, coords = L.grid_from_boxes(starts, counts)
+    assert ggrid == [1, 4, 1] and [c[1] for c in coords] == [0, 1, 2, 3]
+    G = P.global_array(dims, np.float64, kind="index")
+    pencils = []
+    for r, plan in enumerate(plans):
+        assert plan.dims == list(dims) and plan.grid_dims == ggrid
+        gold = L.pencils_from_x(list(dims), ggrid, coords[r], starts[r], counts[r])
+        pencils.append(gold)
+        for d in range(3):
+            got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
+            assert (got.starts, got.counts) == (gold[d].starts, gold[d].counts), (r, d)
+    assert pencils[0][0].size == 0 and pencils[0][1].size > 0
+    for t in (1, -1, 2, -2):
+        si, ri = L.transpose_pencil_ids(t)
+        src = [P.pencil_slice(G, pencils[r][si]) for r in range(n)]
+        want = P.redistribute(G, [pencils[r][ri] for r in range(n)])
+        got = replay_fused(plans, t, src, [w.size for w in want], np.float64)
+        for r in range(n):
+            assert np.array_equal(got[r], want[r]), (t, r)
+        # reference geometry: the empty rank sends / receives nothing
+        d0 = plans[0].describe_exchange(t)
+        if t == 1:
+            assert d0["send_counts"].sum() == 0 and d0["recv_counts"].sum() == pencils[0][1].size
+        if t == -1:
+            assert d0["recv_counts"].sum() == 0
+    Config()._commit()
+
+
 def brick_boxes(cuts):
     """cuts = per axis list of extents; rank order x fastest."""
     edges = [np.concatenate([[0], np.cumsum(c)]) for c in cuts]
