@@ -2,6 +2,7 @@
 #include "handle.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "errors.h"
@@ -98,6 +99,12 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
     nccl_.reset(new NcclBackend);
 
     if (is_transpose_) {
+        // the reference's neighbor_data tables are int32 element offsets: a pencil beyond 2^31 - 1
+        // elements is an INTERNAL_ERROR there (check_if_overflow, :159-172).  Only this path keeps
+        // the limit (NVLINK_FUSED, brick reshapes and single-rank plans use 64-bit boxes).
+        for (int i = 0; i < P; ++i)
+            if (send_by_member[(size_t)i].size() > INT32_MAX || recv_by_member[(size_t)i].size() > INT32_MAX)
+                return DTFFTB_ERROR_INTERNAL;
         geo_ = transpose_geometry(ttype, send_by_member, recv_by_member, me, members, pipelined, false);
         rc = pack_->create(ndims, geo_.send_dims, geo_.pack_kernel, es_, geo_.send_nd.data(), P, ctx_.effort, false);
         if (rc) return rc;

@@ -68,6 +68,10 @@ def product_schedule(descs, inputs, out_sizes, buf_sizes, pipelined):
 @pytest.mark.parametrize("cuts,want_strat,want_free", CASES)
 @pytest.mark.parametrize("pipelined", [False, True])
 def test_reshape_nccl_geometry_and_shortcuts(cuts, want_strat, want_free, pipelined):
+    check_brick_case(cuts, pipelined, want_strat, want_free)
+
+
+def check_brick_case(cuts, pipelined, want_strat=None, want_free=None):
     boxes = brick_boxes(cuts)
     n, nd = len(boxes), len(cuts)
     cfg = Config(enable_fourier_reshape=True, enable_z_slab=False, backend=27 if pipelined else 24,
