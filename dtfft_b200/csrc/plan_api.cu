@@ -2,7 +2,9 @@
 // C / C++ / Fortran bindings call (src/interfaces/api/dtfft_api_c.c:26-461 -> dtfft_api.F90).
 // NULL handling follows dtfft_api_c.c: a NULL plan or NULL out-pointer is
 // DTFFT_ERROR_INVALID_USAGE / DTFFT_ERROR_PLAN_NOT_CREATED.
+#include <mutex>
 #include <new>
+#include <unordered_set>
 
 #include "errors.h"
 #include "plan.h"
@@ -90,19 +92,68 @@ dtfft_error_t dtfft_transpose(dtfft_plan_t plan, void* in, void* out, dtfft_tran
     return E(P(plan)->transpose(in, out, (int)transpose_type, aux));
 }
 // On the GPU every backend enqueues the whole transposition on the plan stream, so *_start
-// does the work and *_end only validates the request (reshape_handle_generic.F90:661-664:
-// async is supported for host MPI backends only).
+// does the work and *_end only validates and retires the request (reshape_handle_generic.F90:661-664:
+// async is supported for host MPI backends only; get_async_active is .false. for the NCCL backends,
+// abstract_backend.F90:345-349, so the *_ACTIVE errors cannot occur here).  A request is the
+// reference's async_request (dtfft_plan.F90:62-72): operation type + buffers, checked by
+// CHECK_REQUEST (:75-84) -- a null, foreign, already retired or wrong-kind request is
+// DTFFT_ERROR_INVALID_REQUEST.  Live requests are kept in a registry so that a stale handle is
+// rejected instead of dereferenced.
+namespace {
+struct AsyncRequest {
+    dtfft_plan_t plan;
+    int type;
+    void *in, *out;
+};
+std::mutex g_req_mutex;
+std::unordered_set<AsyncRequest*> g_requests;
+
+dtfft_request_t new_request(dtfft_plan_t plan, int type, void* in, void* out) {
+    AsyncRequest* r = new (std::nothrow) AsyncRequest{plan, type, in, out};
+    if (!r) return nullptr;
+    std::lock_guard<std::mutex> lk(g_req_mutex);
+    g_requests.insert(r);
+    return r;
+}
+
+dtfft_error_t end_request(dtfft_plan_t plan, dtfft_request_t request, bool transpose) {
+    if (!request) return DTFFT_ERROR_INVALID_REQUEST;
+    AsyncRequest* r = static_cast<AsyncRequest*>(request);
+    std::lock_guard<std::mutex> lk(g_req_mutex);
+    auto it = g_requests.find(r);
+    if (it == g_requests.end()) return DTFFT_ERROR_INVALID_REQUEST;
+    const bool is_transpose = r->type >= -3 && r->type <= 3 && r->type != 0;
+    if (r->plan != plan || is_transpose != transpose || !r->in || !r->out) return DTFFT_ERROR_INVALID_REQUEST;
+    g_requests.erase(it);
+    delete r;
+    return DTFFT_SUCCESS;
+}
+
+void drop_requests_of(dtfft_plan_t plan) {
+    std::lock_guard<std::mutex> lk(g_req_mutex);
+    for (auto it = g_requests.begin(); it != g_requests.end();) {
+        if ((*it)->plan == plan) {
+            delete *it;
+            it = g_requests.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+}  // namespace
+
 dtfft_error_t dtfft_transpose_start(dtfft_plan_t plan, void* in, void* out, dtfft_transpose_t transpose_type,
                                     void* aux, dtfft_request_t* request) {
     if (!request) return DTFFT_ERROR_INVALID_USAGE;
     *request = nullptr;
     dtfft_error_t rc = dtfft_transpose(plan, in, out, transpose_type, aux);
-    if (rc == DTFFT_SUCCESS) *request = plan;
-    return rc;
+    if (rc != DTFFT_SUCCESS) return rc;
+    *request = new_request(plan, (int)transpose_type, in, out);
+    return *request ? DTFFT_SUCCESS : DTFFT_ERROR_ALLOC_FAILED;
 }
 dtfft_error_t dtfft_transpose_end(dtfft_plan_t plan, dtfft_request_t request) {
     PLAN_OR_RETURN(plan);
-    return request == plan ? DTFFT_SUCCESS : DTFFT_ERROR_INVALID_REQUEST;
+    return end_request(plan, request, true);
 }
 dtfft_error_t dtfft_reshape(dtfft_plan_t plan, void* in, void* out, dtfft_reshape_t reshape_type, void* aux) {
     PLAN_OR_RETURN(plan);
@@ -114,17 +165,19 @@ dtfft_error_t dtfft_reshape_start(dtfft_plan_t plan, void* in, void* out, dtfft_
     if (!request) return DTFFT_ERROR_INVALID_USAGE;
     *request = nullptr;
     dtfft_error_t rc = dtfft_reshape(plan, in, out, reshape_type, aux);
-    if (rc == DTFFT_SUCCESS) *request = plan;
-    return rc;
+    if (rc != DTFFT_SUCCESS) return rc;
+    *request = new_request(plan, (int)reshape_type, in, out);
+    return *request ? DTFFT_SUCCESS : DTFFT_ERROR_ALLOC_FAILED;
 }
 dtfft_error_t dtfft_reshape_end(dtfft_plan_t plan, dtfft_request_t request) {
     PLAN_OR_RETURN(plan);
-    return request == plan ? DTFFT_SUCCESS : DTFFT_ERROR_INVALID_REQUEST;
+    return end_request(plan, request, false);
 }
 
 dtfft_error_t dtfft_destroy(dtfft_plan_t* plan) {  // dtfft_api_c.c:190-198: frees and NULLs the handle
     if (!plan || !*plan) return DTFFT_ERROR_PLAN_NOT_CREATED;
     Plan* p = P(*plan);
+    drop_requests_of(*plan);
     p->destroy();
     delete p;
     *plan = nullptr;

@@ -104,6 +104,94 @@ class Platform(IntEnum):
     CUDA = 2
 
 
+class TransposeMode(IntEnum):
+    PACK = 15
+    UNPACK = 16
+
+
+class AccessMode(IntEnum):
+    WRITE = -1
+    READ = 1
+
+
+# Build queries of the reference module (src/interfaces/python/__init__.py:25-72).  This library is the
+# CUDA + NCCL + cuFFT build of the reshape path and nothing else.
+def is_fftw_enabled() -> bool:
+    return False
+
+
+def is_mkl_enabled() -> bool:
+    return False
+
+
+def is_cufft_enabled() -> bool:
+    return True
+
+
+def is_vkfft_enabled() -> bool:
+    return False
+
+
+def is_cuda_enabled() -> bool:
+    return True
+
+
+def is_transpose_only_enabled() -> bool:
+    return False
+
+
+def is_nccl_enabled() -> bool:
+    return True
+
+
+def is_nvshmem_enabled() -> bool:
+    return False
+
+
+def is_compression_enabled() -> bool:
+    return False
+
+
+def get_backend_string(backend) -> str:
+    """String representation of a ``Backend`` value (``dtfft_get_backend_string``)."""
+    s = _lib.lib().dtfft_get_backend_string(int(backend))
+    return s.decode() if s else ""
+
+
+class Version:
+    """dtFFT version this library mirrors (``DTFFT_VERSION_*``, include/dtfft_b200_api.h);
+    ``Version.get()`` asks the loaded library (``dtfft_get_version``: major * 100000 + minor * 1000 + patch)."""
+
+    MAJOR, MINOR, PATCH = 3, 2, 0
+
+    @staticmethod
+    def get() -> int:
+        return int(_lib.lib().dtfft_get_version())
+
+
+class Request:
+    """Async request handle (``dtfft_request_t``) returned by ``transpose_start`` / ``reshape_start``
+    (src/interfaces/python/__init__.py:360-381)."""
+
+    def __init__(self, handle, kind: str):
+        self._handle = int(handle or 0)
+        self._kind = kind
+
+    @property
+    def handle(self) -> int:
+        return self._handle
+
+    @property
+    def kind(self) -> str:
+        return self._kind
+
+    def __int__(self) -> int:
+        return self._handle
+
+    def __repr__(self) -> str:
+        return f"Request(kind={self._kind!r}, handle=0x{self._handle:x})"
+
+
 class DtfftError(RuntimeError):
     """Non-zero ``dtfft_error_t`` (same codes as the reference, include/dtfft_config.h.in:82-151)."""
 
@@ -222,6 +310,26 @@ class _DeviceBuffer:
             self._plan.mem_free(self)
         self.ptr = 0
 
+    _owned = False  # set by Plan.get_ndarray: the array owns the allocation
+
+    def __del__(self):
+        if self._owned:
+            try:
+                self.free()
+            except Exception:
+                pass
+
+
+def _shaped_view(flat, shape, order):
+    """View of the first prod(shape) elements of a flat tensor as ``shape`` in C or Fortran order."""
+    n = 1
+    for v in shape:
+        n *= v
+    flat = flat[:n]
+    if order == "C":
+        return flat.view(shape)
+    return flat.view(shape[::-1]).permute(*range(len(shape) - 1, -1, -1))
+
 
 class Plan:
     """Base plan wrapper (reference: ``class Plan``, src/interfaces/python/__init__.py:396-720)."""
@@ -283,19 +391,21 @@ class Plan:
         req = C.c_void_p(0)
         _check(_lib.lib().dtfft_transpose_start(self._h, _ptr(inbuf), _ptr(outbuf), int(transpose_type),
                                                 _ptr(aux) or None, C.byref(req)), "dtfft_transpose_start")
-        return req
+        return Request(req.value, str(Transpose(int(transpose_type))))
 
     def transpose_end(self, request):
-        _check(_lib.lib().dtfft_transpose_end(self._h, request), "dtfft_transpose_end")
+        handle = request.handle if isinstance(request, Request) else int(getattr(request, "value", request) or 0)
+        _check(_lib.lib().dtfft_transpose_end(self._h, C.c_void_p(handle)), "dtfft_transpose_end")
 
     def reshape_start(self, inbuf, outbuf, reshape_type: Reshape, aux=None):
         req = C.c_void_p(0)
         _check(_lib.lib().dtfft_reshape_start(self._h, _ptr(inbuf), _ptr(outbuf), int(reshape_type), _ptr(aux) or None,
                                               C.byref(req)), "dtfft_reshape_start")
-        return req
+        return Request(req.value, str(Reshape(int(reshape_type))))
 
     def reshape_end(self, request):
-        _check(_lib.lib().dtfft_reshape_end(self._h, request), "dtfft_reshape_end")
+        handle = request.handle if isinstance(request, Request) else int(getattr(request, "value", request) or 0)
+        _check(_lib.lib().dtfft_reshape_end(self._h, C.c_void_p(handle)), "dtfft_reshape_end")
 
     # ---- metadata -------------------------------------------------------------------------
     def _size_t(self, name) -> int:
@@ -376,6 +486,45 @@ class Plan:
         _check(_lib.lib().dtfft_mem_free(self._h, ptr), "dtfft_mem_free")
         if isinstance(buf, _DeviceBuffer):
             buf.ptr = 0
+
+    @property
+    def dtype(self):
+        """Plan-native element type (src/interfaces/python/__init__.py:472-476): complex for C2C plans,
+        real otherwise, width from ``element_size``."""
+        import numpy as np
+
+        es = self.element_size
+        if self._KIND == "c2c":
+            return np.dtype(np.complex128 if es == 16 else np.complex64)
+        return np.dtype(np.float64 if es == 8 else np.float32)
+
+    def get_ndarray(self, size: int, shape=None, dtype=None, order: str = "C"):
+        """Array backed by plan-managed device memory (``dtfft_mem_alloc``), freed when the last view of it
+        dies -- the reference's ``Plan.get_ndarray`` (src/interfaces/python/__init__.py:656-706) with a CUDA
+        ``torch.Tensor`` in place of the ``cupy.ndarray`` (there is no host platform here).  ``size`` elements
+        are allocated; ``shape`` may cover fewer.  ``order='F'`` gives the column-major view dtFFT's layouts
+        are described in (``shape[0]`` fastest)."""
+        import math
+
+        import numpy as np
+        import torch
+
+        if shape is None:
+            shape = (int(size),)
+        elif isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(int(v) for v in shape)
+        if math.prod(shape) > size:
+            raise ValueError(f"Shape {shape} is too large for requested size {size}")
+        if order not in ("C", "F"):
+            raise ValueError("order must be 'C' or 'F'")
+        np_dtype = np.dtype(self.dtype if dtype is None else dtype)
+        tdtype = {"float32": torch.float32, "float64": torch.float64, "complex64": torch.complex64,
+                  "complex128": torch.complex128, "uint8": torch.uint8, "int32": torch.int32,
+                  "int64": torch.int64}[np_dtype.name]
+        buf = self.mem_alloc(int(size) * np_dtype.itemsize)
+        buf._owned = True  # freed by __del__ of the buffer object, which the tensor's storage keeps alive
+        return _shaped_view(torch.as_tensor(buf, device="cuda").view(tdtype), shape, order)
 
     def register_buffer(self, buf, nbytes: int | None = None):
         """NVLINK_FUSED backend: make a user-allocated device buffer reachable by the peers (collective)."""

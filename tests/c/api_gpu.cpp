@@ -91,8 +91,16 @@ static void transpose_only_3d() {
     EXPECT(plan.transpose(h_in.data(), b, Transpose::X_TO_Y) == Error::NOT_DEVICE_PTR);
     EXPECT(plan.execute(a, b, static_cast<Execute>(3)) == Error::INVALID_EXECUTE_TYPE);
     EXPECT(plan.reshape(a, b, Reshape::X_BRICKS_TO_PENCILS) == Error::RESHAPE_NOT_SUPPORTED);
+    // async requests (dtfft_plan.F90:599-693; CHECK_REQUEST :75-84): a request is retired once, by the
+    // plan and the kind of call that started it
     dtfft_request_t req = plan.transpose_start(a, b, Transpose::X_TO_Y);
+    EXPECT(req != nullptr);
+    EXPECT(plan.reshape_end(req) == Error::INVALID_REQUEST);      // a transposition, not a reshape
     EXPECT(plan.transpose_end(req) == Error::SUCCESS);
+    EXPECT(plan.transpose_end(req) == Error::INVALID_REQUEST);    // already retired
+    EXPECT(plan.transpose_end(nullptr) == Error::INVALID_REQUEST);
+    dtfft_request_t none = nullptr;
+    EXPECT(plan.transpose_start(a, a, Transpose::X_TO_Y, &none) == Error::INPLACE_TRANSPOSE && none == nullptr);
     const Plan::Stats st = plan.get_stats();
     EXPECT(st.kernel_launches >= 1 && st.local_bytes == (int64_t)(n * sizeof(cd)) && st.remote_bytes == 0);
     CUDA_OK(cudaStreamSynchronize(stream));

@@ -434,3 +434,44 @@ def test_grid_search_redecomposition_equals_cart_grid(dims, nranks):
                 for key in ("send_nd", "recv_nd", "send_counts", "send_displs", "recv_counts", "recv_displs"):
                     assert np.array_equal(da[key], db[key]), key
                 assert (da["pack_kernel"], da["unpack_kernel"]) == (db["pack_kernel"], db["unpack_kernel"])
+
+
+def test_python_api_surface_of_the_reference_module():
+    """Names a user of the reference's Python package relies on (src/interfaces/python/__init__.py:
+    25-72 build queries, 112-115 exception / version, 360-381 Request, 708-710 dtype) exist with the
+    same meaning; values are those of this build (CUDA + NCCL + cuFFT, nothing else)."""
+    import dtfft_b200 as d
+
+    assert d.is_cuda_enabled() and d.is_cufft_enabled() and d.is_nccl_enabled()
+    assert not (d.is_fftw_enabled() or d.is_mkl_enabled() or d.is_vkfft_enabled() or d.is_nvshmem_enabled()
+                or d.is_compression_enabled() or d.is_transpose_only_enabled())
+    assert d.get_backend_string(d.Backend.NCCL) == "NCCL"
+    assert d.get_backend_string(d.Backend.NCCL_PIPELINED) == "NCCL_PIPELINED"
+    assert d.Version.get() == d.Version.MAJOR * 100000 + d.Version.MINOR * 1000 + d.Version.PATCH
+    assert d.dtfft_Exception is d.DtfftError
+    assert (d.TransposeMode.PACK, d.TransposeMode.UNPACK, d.AccessMode.WRITE, d.AccessMode.READ) == (15, 16, -1, 1)
+    assert PlanC2C([8, 8, 8], dry=True).dtype == np.complex128
+    assert PlanC2C([8, 8, 8], precision=Precision.SINGLE, dry=True).dtype == np.complex64
+    assert PlanR2R([8, 8, 8], dry=True).dtype == np.float64
+    assert PlanR2C([8, 8, 8], precision=Precision.SINGLE, executor=Executor.CUFFT, dry=True).dtype == np.float32
+    r = d.Request(0x1234, "Transpose.X_TO_Y")
+    assert int(r) == r.handle == 0x1234 and r.kind == "Transpose.X_TO_Y" and "0x1234" in repr(r)
+    # a request nobody started is rejected (CHECK_REQUEST, src/dtfft_plan.F90:75-84)
+    p = PlanC2C([8, 8, 8], dry=True)
+    for bad in (d.Request(0, "x"), d.Request(0xdead0, "x")):
+        with pytest.raises(DtfftError) as e:
+            p.transpose_end(bad)
+        assert e.value.code == 35  # DTFFT_ERROR_INVALID_REQUEST
+    with pytest.raises(ValueError):
+        p.get_ndarray(8, shape=(3, 3))
+    # shape / order handling of get_ndarray (the allocation itself needs a GPU: tests/test_zz_python_api_gpu.py)
+    import torch
+
+    from dtfft_b200.plan import _shaped_view
+
+    flat = torch.arange(40, dtype=torch.float64)
+    f = _shaped_view(flat, (2, 3, 4), "F")
+    assert tuple(f.shape) == (2, 3, 4) and f.stride() == (1, 2, 6) and f[1, 2, 3] == 1 + 2 * 2 + 3 * 6
+    c = _shaped_view(flat, (2, 3, 4), "C")
+    assert c.stride() == (12, 4, 1) and c[1, 2, 3] == 23
+    assert f.data_ptr() == flat.data_ptr() == c.data_ptr()
