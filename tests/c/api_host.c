@@ -105,6 +105,10 @@ int main(void) {
     void* ptr = NULL;
     EXPECT(dtfft_mem_alloc(plan, 1024, &ptr) == DTFFT_ERROR_GPU_NOT_SET); /* a dry plan never touches a device */
     EXPECT(dtfft_execute(plan, dummy, dummy + 1, DTFFT_EXECUTE_FORWARD, NULL) == DTFFT_ERROR_GPU_NOT_SET);
+    /* async requests: nothing was started, so nothing can be retired (CHECK_REQUEST, dtfft_plan.F90:75-84) */
+    EXPECT(dtfft_transpose_end(plan, NULL) == DTFFT_ERROR_INVALID_REQUEST);
+    EXPECT(dtfft_reshape_end(plan, (dtfft_request_t)dummy) == DTFFT_ERROR_INVALID_REQUEST);
+    EXPECT(dtfft_transpose_start(plan, dummy, dummy + 1, DTFFT_TRANSPOSE_X_TO_Y, NULL, NULL) == DTFFT_ERROR_INVALID_USAGE);
     EXPECT(dtfft_destroy(&plan) == DTFFT_SUCCESS && plan == NULL);
 
     /* dry R2C plan: the complex side has nx/2+1 points along x */

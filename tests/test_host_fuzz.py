@@ -6,7 +6,7 @@ and tests/test_reshape_shortcuts.py, on shapes nobody picked by hand."""
 import numpy as np
 import pytest
 
-from dtfft_b200.plan import Config, Pencil, PlanC2C
+from dtfft_b200.plan import Config, Executor, Layout, Pencil, PlanC2C, PlanR2C, Precision
 from oracle import layout as L
 from oracle import pipeline as P
 from tests.test_plan_host import LAYOUT_OF_PENCIL, dry_world, replay_fused
@@ -149,3 +149,52 @@ def _brick_cases(n_cases, seed):
 @pytest.mark.parametrize("cuts,pipelined", _brick_cases(25, 11))
 def test_random_bricks(cuts, pipelined):
     check_brick_case(cuts, pipelined)
+
+
+def _r2c_cases(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_cases):
+        nd = int(rng.choice([2, 3]))
+        nranks = int(rng.choice([1, 2, 4, 6]))
+        dims = [int(v) for v in rng.integers(2 * max(2, nranks), 36, size=nd)]
+        out.append((dims, nranks, bool(rng.integers(0, 2)), bool(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("dims,nranks,z_slab,single", _r2c_cases(16, 3))
+def test_random_r2c_plans(dims, nranks, z_slab, single):
+    """R2C: the real X pencil keeps the user's dims, every complex pencil has nx/2 + 1 points along x
+    (src/dtfft_plan.F90:2626-2630); sizes are counted in REAL elements (:1350-1355, 1868-1876) and every
+    transposition of the complex side reproduces the datatype path."""
+    nd = len(dims)
+    prec = Precision.SINGLE if single else Precision.DOUBLE
+    cfg = Config(enable_z_slab=z_slab)
+    plans = dry_world(nranks, lambda r, c: PlanR2C(list(dims), comm=c, precision=prec, executor=Executor.CUFFT,
+                                                   config=cfg, dry=True))
+    cdims = [dims[0] // 2 + 1] + list(dims[1:])
+    comm_dims = plans[0].grid_dims
+    want_dims, is_z, _ = L.choose_grid(cdims, nranks, cuda=True, z_slab=z_slab, y_slab=False)
+    assert comm_dims == want_dims and plans[0].z_slab_enabled == is_z
+    es_real = 4 if single else 8
+    for r, plan in enumerate(plans):
+        gold = L.make_pencils(cdims, comm_dims, r)
+        real = plan.get_pencil(Layout.X_PENCILS)
+        assert real.counts == [dims[0]] + gold[0].counts[1:] and real.starts == gold[0].starts
+        four = plan.get_pencil(Layout.X_PENCILS_FOURIER)
+        assert (four.starts, four.counts) == (gold[0].starts, gold[0].counts)
+        for d in range(1, nd):
+            got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
+            assert (got.starts, got.counts) == (gold[d].starts, gold[d].counts), (r, d)
+        assert plan.element_size == es_real
+        assert plan.alloc_size == max(int(np.prod(real.counts)), 2 * max(p.size for p in gold))
+        assert plan.alloc_bytes == plan.alloc_size * es_real
+    G = P.global_array(cdims, np.complex128, kind="index")
+    ttypes = [1, -1] if nd == 2 else [1, -1, 2, -2] + ([3, -3] if is_z else [])
+    for t in ttypes:
+        src = P.scatter_input(G, cdims, comm_dims, t)
+        want = P.transpose_datatype(G, cdims, comm_dims, t)
+        got = replay_fused(plans, t, src, [w.size for w in want], np.complex128)
+        for r in range(nranks):
+            assert np.array_equal(got[r], want[r]), (L.TRANSPOSE_NAMES[t], r)
+    Config()._commit()
