@@ -29,11 +29,44 @@ def time_ms(fn, warmup=3, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def quick(args):
+    n = args.n
+    N = n ** 3
+    hint = os.environ.get("DTFFTB_CACHE_HINT", "0")
+    for es in (16, 8, 4):
+        a = torch.empty(N * es, dtype=torch.uint8, device="cuda")
+        a.random_(0, 255)
+        b = torch.empty_like(a)
+        gb = 2 * N * es / 1e9
+        for kt, name in ((KERNEL_PERMUTE_FORWARD, "forward"), (KERNEL_PERMUTE_BACKWARD, "backward"),
+                         (KERNEL_PERMUTE_BACKWARD_START, "backward_start")):
+            k = Kernel().create([n, n, n], 0, es, kt)
+            ms = time_ms(lambda: k.execute(a, b), warmup=5, iters=20)
+            print(json.dumps({"what": name, "es": es, "n": n, "cache_hint": hint, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
+            k.destroy()
+        P = 8
+        nxx = n // P
+        nd = np.zeros((P, 5), dtype=np.int32)
+        for i in range(P):
+            nd[i] = (nxx, n, n, i * nxx * n * n, i * nxx)
+        for kt, name in ((KERNEL_UNPACK, "unpack8"), (KERNEL_PERMUTE_BACKWARD_END, "backward_end8")):
+            k = Kernel().create([n, n, n], 0, es, kt, nd)
+            ms = time_ms(lambda: k.execute(a, b), warmup=5, iters=20)
+            print(json.dumps({"what": name, "es": es, "n": n, "cache_hint": hint, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
+            k.destroy()
+        del a, b
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--out", default="gpurun_out/kbench.jsonl")
+    ap.add_argument("--quick", action="store_true",
+                    help="default tile / grid of every kernel only (A/B of process-wide switches such as DTFFTB_CACHE_HINT)")
     args = ap.parse_args()
+    if args.quick:
+        return quick(args)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     f = open(args.out, "a")
 

@@ -1,0 +1,10 @@
+# Round 2, first 2-GPU call:  gpurun --gpus 2 --timeout 900 -- 'bash tools/r02_n2.sh'
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+# 1. every backend through the plan API, brick reshapes with and without the pack-free / unpack-free shortcuts
+timeout 500 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -30
+# 2. config 5 (bricks, NCCL backends): shortcuts on / off
+for s in 1 0; do DTFFTB_RESHAPE_SHORTCUTS=$s timeout 300 $TR --master-port 2952$s tools/configs_bench.py --configs c5 --backends nccl,nccl_pipe --overlap 1 > gpurun_out/r02a_c5_shortcuts${s}_n2.jsonl 2> gpurun_out/r02a_c5_shortcuts${s}_n2.err; cut -c 1-330 gpurun_out/r02a_c5_shortcuts${s}_n2.jsonl; tail -3 gpurun_out/r02a_c5_shortcuts${s}_n2.err; done
+# 3. CUDA-graph replay of the NCCL backends on the launch-bound half-size configs
+for g in 0 1; do DTFFTB_GRAPHS_NCCL=$g timeout 300 $TR --master-port 2953$g tools/configs_bench.py --configs c2fft,c4 --backends nccl,nccl_pipe --overlap 1 --scale 0.5 > gpurun_out/r02a_half_ncclgraphs${g}_n2.jsonl 2> gpurun_out/r02a_half_ncclgraphs${g}_n2.err; cut -c 1-330 gpurun_out/r02a_half_ncclgraphs${g}_n2.jsonl; tail -3 gpurun_out/r02a_half_ncclgraphs${g}_n2.err; done
+# 4. the bench line
+timeout 300 $TR --master-port 29540 bench.py --gpus 2 > gpurun_out/r02a_bench_n2.json 2> gpurun_out/r02a_bench_n2.err; cut -c 1-600 gpurun_out/r02a_bench_n2.json; tail -3 gpurun_out/r02a_bench_n2.err

@@ -1,0 +1,7 @@
+# Round 2, 8-GPU call:  gpurun --gpus 8 --timeout 900 -- 'bash tools/r02_n8.sh'
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+# 1. first run of the process-grid search on real GPUs: 512^3 at 8 ranks, 1x8 vs 8x1 vs 2x4 vs 4x2
+DTFFTB_LOG=1 timeout 300 $TR --master-port 29551 tools/grid_search_probe.py > gpurun_out/r02a_grid_search_n8.txt 2>&1; tail -25 gpurun_out/r02a_grid_search_n8.txt
+# 2. multi-GPU suite (fused backend only keeps it short) and the bench line
+DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -15
+timeout 300 $TR --master-port 29552 bench.py --gpus 8 > gpurun_out/r02a_bench_n8.json 2> gpurun_out/r02a_bench_n8.err; cut -c 1-700 gpurun_out/r02a_bench_n8.json; tail -3 gpurun_out/r02a_bench_n8.err
