@@ -300,6 +300,25 @@ int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStre
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
 
+int PeerRegistry::reset_barriers() {
+    if (!inited_ || !available_ || !flags_ || world_.size() == 1) return DTFFT_SUCCESS;
+    cudaError_t ce = cudaDeviceSynchronize();  // my barriers have completed ...
+    if (ce != cudaSuccess) return cuda_error(ce);
+    world_.barrier();                          // ... and so have everybody's: nobody reads or writes flags now
+    for (auto& kv : groups_) {
+        if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
+        if (kv.second.d_members) cudaFree(kv.second.d_members);
+        if (kv.second.d_epoch) cudaFree(kv.second.d_epoch);
+    }
+    groups_.clear();
+    ce = cudaMemset(flags_, 0, (size_t)kChannels * world_.size() * sizeof(uint64_t));  // the error word stays
+    if (ce != cudaSuccess) return cuda_error(ce);
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) return cuda_error(ce);
+    world_.barrier();  // no peer may signal before my flags are clean
+    return DTFFT_SUCCESS;
+}
+
 int PeerRegistry::error_state() {
     if (!flags_) return 0;
     uint64_t v = 0;

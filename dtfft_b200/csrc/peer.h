@@ -45,6 +45,10 @@ public:
     // Enqueue a barrier among `members` (world ranks, must contain me) on `stream`.
     // `channel` separates independent groups (1-D communicator id 1..3, x2 phases).
     int barrier(const std::vector<int>& members, int channel, cudaStream_t stream);
+    // Collective.  Forget every barrier group and zero the flags: must be called when the 1-D
+    // communicators change (process-grid search), because a new group starts at epoch 0 while the
+    // flag rows of its channel may still hold the last epoch of a differently composed group.
+    int reset_barriers();
     // Non-zero if a barrier ever timed out (peer missing); sticky.
     int error_state();
     void destroy();

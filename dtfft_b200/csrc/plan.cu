@@ -819,6 +819,8 @@ int Plan::autotune_grid(bool all_backends) {
     int best_b = backend_, best1 = saved1, best2 = saved2;
     for (const auto& g : grids) {
         set_grid(g.first, g.second);
+        int rcb = peers_.reset_barriers();  // the 1-D communicators just changed
+        if (rcb) return rcb;
         for (int b : backends) {
             double ms = 1e30;
             int rc = time_backend(b, &ms);
@@ -829,6 +831,8 @@ int Plan::autotune_grid(bool all_backends) {
     }
     // nothing could be timed (no valid grid): keep the default decomposition (transpose_plan.F90:502-525)
     set_grid(best1, best2);
+    int rcb = peers_.reset_barriers();
+    if (rcb) return rcb;
     backend_ = best_b;
     log("DTFFT_MEASURE: selected process grid 1x%dx%d", best1, best2);
     if (all_backends) log("DTFFT_PATIENT: selected backend is %s", dtfft_get_backend_string((dtfft_backend_t)backend_));
