@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
     L.dtfftb_kernel_get_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 5 + [i64p]
     L.dtfftb_kernel_set_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.dtfftb_kernel_autotune.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.dtfftb_kernel_create_dry.argtypes = [C.POINTER(vp), C.c_int, i32p, C.c_int, C.c_int64, i32p, C.c_int]
+    L.dtfftb_kernel_create_boxes_dry.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.c_int, i64p, C.c_int]
+    L.dtfftb_kernel_dump_table.argtypes = [vp, C.c_int, C.c_int, C.c_int32, i64p, i32p, i64p, i32p]
+    for name in ("dtfftb_kernel_create_dry", "dtfftb_kernel_create_boxes_dry", "dtfftb_kernel_dump_table"):
+        getattr(L, name).restype = C.c_int
     for name in ("dtfftb_kernel_create", "dtfftb_kernel_execute", "dtfftb_kernel_execute_all",
                  "dtfftb_kernel_set_peer_out", "dtfftb_kernel_destroy", "dtfftb_kernel_get_info",
                  "dtfftb_kernel_set_tile", "dtfftb_kernel_autotune"):

@@ -1,7 +1,9 @@
 // C ABI shell over dtfftb::Kernel (declared in include/dtfft_b200.h).
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <new>
+#include <vector>
 
 #include "../../include/dtfft_b200.h"
 #include "errors.h"
@@ -35,6 +37,75 @@ int dtfftb_kernel_create(dtfftb_kernel_t* kernel, int ndims, const int32_t* dims
         return rc;
     }
     *kernel = h;
+    return DTFFT_SUCCESS;
+}
+
+int dtfftb_kernel_create_dry(dtfftb_kernel_t* kernel, int ndims, const int32_t* dims, int kernel_type,
+                             int64_t base_storage, const int32_t* neighbor_data, int n_neighbors) {
+    if (!kernel) return DTFFT_ERROR_INVALID_USAGE;
+    *kernel = nullptr;
+    dtfftb_kernel_s* h = new (std::nothrow) dtfftb_kernel_s;
+    if (!h) return DTFFT_ERROR_ALLOC_FAILED;
+    h->k.set_dry(true);
+    int rc = h->k.create(ndims, dims, kernel_type, base_storage, neighbor_data, n_neighbors, 0, false);
+    if (rc != DTFFT_SUCCESS) {
+        delete h;
+        return rc;
+    }
+    *kernel = h;
+    return DTFFT_SUCCESS;
+}
+
+int dtfftb_kernel_create_boxes_dry(dtfftb_kernel_t* kernel, int family, int64_t base_storage, int n_boxes,
+                                   const int64_t* boxes, int remote_peers) {
+    if (!kernel || !boxes || n_boxes <= 0) return DTFFT_ERROR_INVALID_USAGE;
+    *kernel = nullptr;
+    dtfftb_kernel_s* h = new (std::nothrow) dtfftb_kernel_s;
+    if (!h) return DTFFT_ERROR_ALLOC_FAILED;
+    h->k.set_dry(true);
+    std::vector<dtfftb::Box> bx((size_t)n_boxes);
+    for (int i = 0; i < n_boxes; ++i) {
+        const int64_t* o = boxes + 10 * i;
+        dtfftb::Box& b = bx[(size_t)i];
+        b.n0 = o[0], b.n1 = o[1], b.n2 = o[2], b.in_off = o[3], b.out_off = o[4];
+        b.is1 = o[5], b.is2 = o[6], b.os0 = o[7], b.os1 = o[8], b.os2 = o[9];
+    }
+    int rc = h->k.create_boxes((dtfftb::Family)family, base_storage, bx);
+    if (rc == DTFFT_SUCCESS && remote_peers && !h->k.is_noop()) {
+        // stand-ins for peer-mapped destination bases: box i is written to "peer i + 1"
+        std::vector<void*> bases((size_t)n_boxes);
+        for (int i = 0; i < n_boxes; ++i) bases[(size_t)i] = reinterpret_cast<void*>((uintptr_t)(i + 1) << 40);
+        rc = h->k.set_peer_out(bases.data(), nullptr);
+    }
+    if (rc != DTFFT_SUCCESS) {
+        delete h;
+        return rc;
+    }
+    *kernel = h;
+    return DTFFT_SUCCESS;
+}
+
+int dtfftb_kernel_dump_table(dtfftb_kernel_t kernel, int unit, int neighbor, int32_t cap, int64_t* rows,
+                             int32_t* n_blocks, int64_t* total_items, int32_t* launch) {
+    if (!kernel || !n_blocks || !total_items || !launch) return DTFFT_ERROR_INVALID_USAGE;
+    if (!kernel->k.dry()) return DTFFT_ERROR_INVALID_USAGE;
+    *n_blocks = 0, *total_items = 0;
+    dtfftb::DeviceTable t;
+    int l3[3] = {0, 0, 0};
+    const dtfftb::BlockDesc* b = kernel->k.host_table(unit, neighbor, &t, l3);
+    if (!b) return DTFFT_SUCCESS;  // no such table (no-op kernel, copy kernel, unit too wide)
+    *n_blocks = t.nblocks, *total_items = t.total_items;
+    for (int i = 0; i < 3; ++i) launch[i] = l3[i];
+    if (!rows || cap < t.nblocks) return DTFFT_SUCCESS;
+    for (int i = 0; i < t.nblocks; ++i) {
+        const dtfftb::BlockDesc& d = b[i];
+        int64_t* o = rows + 20 * i;
+        o[0] = d.in_off, o[1] = d.out_off, o[2] = d.is1, o[3] = d.is2, o[4] = d.os0, o[5] = d.os1, o[6] = d.os2;
+        o[7] = d.item_begin, o[8] = d.shuffle, o[9] = d.n0, o[10] = d.n1, o[11] = d.n2, o[12] = d.tiles0, o[13] = d.tiles1;
+        o[14] = d.div0.mul, o[15] = d.div0.shr, o[16] = d.div1.mul, o[17] = d.div1.shr;
+        o[18] = d.out_base ? (int64_t)((uintptr_t)d.out_base >> 40) - 1 : -1;
+        o[19] = 0;
+    }
     return DTFFT_SUCCESS;
 }
 

@@ -284,11 +284,13 @@ int Kernel::create(int ndims, const int32_t* dims, int kernel_type, int64_t base
     }
     noop_ = false;
 
-    int dev = 0;
-    cudaError_t ce = cudaGetDevice(&dev);
-    if (ce != cudaSuccess) return cuda_error(ce);
-    ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
-    if (ce != cudaSuccess) return cuda_error(ce);
+    if (!dry_) {
+        int dev = 0;
+        cudaError_t ce = cudaGetDevice(&dev);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
+        if (ce != cudaSuccess) return cuda_error(ce);
+    }
 
     if (family_ == FAM_COPY) return DTFFT_SUCCESS;
 
@@ -313,7 +315,7 @@ int Kernel::create(int ndims, const int32_t* dims, int kernel_type, int64_t base
     int rc = rebuild_tables();
     if (rc != DTFFT_SUCCESS) return rc;
 
-    if (effort >= 3 /* DTFFT_EXHAUSTIVE */ && family_ == FAM_T) {
+    if (effort >= 3 /* DTFFT_EXHAUSTIVE */ && family_ == FAM_T && !dry_) {
         // Timed kernel autotune on scratch buffers (kernel_device.F90:338-397).
         long long elems = 0, in_need = 0, out_need = 0;
         for (auto& b : boxes_) {
@@ -352,11 +354,13 @@ int Kernel::create_boxes(Family family, int64_t base_storage, const std::vector<
     for (auto& b : boxes_) any |= !b.empty();
     noop_ = !any;
     if (noop_) return DTFFT_SUCCESS;
-    int dev = 0;
-    cudaError_t ce = cudaGetDevice(&dev);
-    if (ce != cudaSuccess) return cuda_error(ce);
-    ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
-    if (ce != cudaSuccess) return cuda_error(ce);
+    if (!dry_) {
+        int dev = 0;
+        cudaError_t ce = cudaGetDevice(&dev);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev);
+        if (ce != cudaSuccess) return cuda_error(ce);
+    }
     if (family_ == FAM_T) {
         tile_ = default_tile((int)es_);
         if (const char* e = getenv("DTFFTB_TILE")) {
@@ -371,6 +375,7 @@ int Kernel::create_boxes(Family family, int64_t base_storage, const std::vector<
 int Kernel::rebuild_tables() {
     if (d_blocks_) cudaFree(d_blocks_);
     d_blocks_ = nullptr;
+    host_tables_.clear();
     std::vector<BlockDesc> host;
     // CTAs per resident slot.  Measured on B200 (profiles/r01_kbench.md): a static persistent
     // partition (1) loses ~7 % to SMs that finish early; one CTA per tile (0 = no cap, the
@@ -515,6 +520,10 @@ int Kernel::rebuild_tables() {
             host[(size_t)t.offset].shuffle = s;
         }
     }
+    if (dry_) {
+        host_tables_ = host;
+        return DTFFT_SUCCESS;
+    }
     if (!host.empty()) {
         cudaError_t ce = cudaMalloc(&d_blocks_, host.size() * sizeof(BlockDesc));
         if (ce != cudaSuccess) return cuda_error(ce);
@@ -522,6 +531,29 @@ int Kernel::rebuild_tables() {
         if (ce != cudaSuccess) return cuda_error(ce);
     }
     return DTFFT_SUCCESS;
+}
+
+const BlockDesc* Kernel::host_table(int unit, int neighbor, DeviceTable* t, int launch[3]) const {
+    if (!dry_ || !created_ || noop_ || (family_ != FAM_T && family_ != FAM_R)) return nullptr;
+    int slot = 0;
+    if (family_ == FAM_R) {
+        if (unit != 4 && unit != 8 && unit != 16) return nullptr;
+        if (unit > unit_geo_) return nullptr;
+        slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
+        launch[0] = tx_slot_[slot], launch[1] = kRowsThreads / tx_slot_[slot], launch[2] = kRowsPerThread;
+    } else {
+        launch[0] = tile_.ka, launch[1] = tile_.kb, launch[2] = tile_.rows;
+    }
+    const DeviceTable* dt = nullptr;
+    if (neighbor == 0) {
+        dt = &all_[slot];
+    } else {
+        if (neighbor < 1 || neighbor > (int)single_[slot].size()) return nullptr;
+        dt = &single_[slot][(size_t)(neighbor - 1)];
+    }
+    *t = *dt;
+    if (dt->nblocks == 0) return host_tables_.data();  // empty table: nothing to launch
+    return host_tables_.data() + dt->offset;
 }
 
 int Kernel::pick_unit(const void* in, const void* out) const {
@@ -551,6 +583,7 @@ int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cu
 
 int Kernel::execute(const void* in, void* out, cudaStream_t stream, int neighbor, bool sync) {
     if (!created_) return DTFFTB_ERROR_INTERNAL;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (noop_) return DTFFT_SUCCESS;  // abstract_kernel.F90:310
     if (!in || !out) return DTFFT_ERROR_INVALID_USAGE;
     int rc = DTFFT_SUCCESS;
@@ -595,6 +628,7 @@ int Kernel::execute(const void* in, void* out, cudaStream_t stream, int neighbor
 
 int Kernel::execute_all(const void* in, void* out, cudaStream_t stream) {
     if (!created_) return DTFFTB_ERROR_INTERNAL;
+    if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (noop_) return DTFFT_SUCCESS;
     if (family_ == FAM_COPY) {
         if (type_ == K_COPY) return execute(in, out, stream, 0, false);

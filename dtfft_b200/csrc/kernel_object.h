@@ -75,6 +75,15 @@ public:
     int autotune(const void* in, void* out, cudaStream_t stream, int n_warmup, int n_iters, float* best_ms);
     void destroy();
 
+    // Host-only mode (tests on CPU boxes): geometry and tables are built exactly as for a launch but
+    // nothing touches a device; execute() fails.  Set BEFORE create / create_boxes.
+    void set_dry(bool d) { dry_ = d; }
+    bool dry() const { return dry_; }
+    // The table a launch would hand to the device (dry kernels only): family R `unit` in {4, 8, 16}
+    // (ignored for family T), `neighbor` 1-based or 0 for the all-peer table.  Returns nullptr when
+    // the table does not exist (unit wider than the geometry allows).
+    const BlockDesc* host_table(int unit, int neighbor, DeviceTable* t, int launch[3]) const;
+
     bool is_noop() const { return noop_; }
     Family family() const { return family_; }
     int type() const { return type_; }
@@ -90,7 +99,8 @@ private:
     int launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream);
     int pick_unit(const void* in, const void* out) const;
 
-    bool created_ = false, noop_ = true, custom_ = false;
+    bool created_ = false, noop_ = true, custom_ = false, dry_ = false;
+    std::vector<BlockDesc> host_tables_;  // dry mode: what would have been uploaded
     int ndims_ = 0, type_ = K_DUMMY, P_ = 0;
     int32_t dims_[3] = {1, 1, 1};
     int64_t es_ = 0;

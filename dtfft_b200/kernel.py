@@ -88,6 +88,48 @@ class Kernel:
         self.neighbor_data = None if neighbor_data is None else np.asarray(neighbor_data, dtype=np.int32).reshape(-1, 5)
         return self
 
+    def create_dry(self, dims, base_storage, kernel_type, neighbor_data=None):
+        """Host-only twin of :meth:`create` (``dtfftb_kernel_create_dry``): same geometry and work-item
+        tables, no device; for CPU tests of the table builder (:meth:`dump_table`)."""
+        self.destroy()
+        L = _lib.lib()
+        dims_arr = (C.c_int32 * len(dims))(*[int(d) for d in dims])
+        nd_ptr, n_nb = None, 0
+        if neighbor_data is not None:
+            nd = np.ascontiguousarray(np.asarray(neighbor_data, dtype=np.int32).reshape(-1, 5))
+            n_nb = nd.shape[0]
+            self._nd_keep = nd
+            nd_ptr = nd.ctypes.data_as(C.POINTER(C.c_int32))
+        _lib.check(L.dtfftb_kernel_create_dry(C.byref(self._h), len(dims), dims_arr, int(kernel_type), int(base_storage),
+                                              nd_ptr, n_nb), "dtfftb_kernel_create_dry")
+        self.dims, self.kernel_type, self.base_storage = list(dims), int(kernel_type), int(base_storage)
+        return self
+
+    def create_boxes_dry(self, family: int, base_storage, boxes, remote_peers=False):
+        """Host-only kernel over explicit boxes (rows of n0 n1 n2 in_off out_off is1 is2 os0 os1 os2), as
+        the plan layer builds for the fused NVLink path (family 2 or 3) and the brick reshapes (family 3)."""
+        self.destroy()
+        bx = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 10))
+        _lib.check(_lib.lib().dtfftb_kernel_create_boxes_dry(C.byref(self._h), int(family), int(base_storage), bx.shape[0],
+                                                             bx.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                             int(bool(remote_peers))), "dtfftb_kernel_create_boxes_dry")
+        self.base_storage = int(base_storage)
+        return self
+
+    def dump_table(self, unit=0, neighbor=0) -> dict:
+        """Work-item table of one launch of a dry kernel (``dtfftb_kernel_dump_table``)."""
+        L = _lib.lib()
+        nb, total = C.c_int32(0), C.c_int64(0)
+        launch = (C.c_int32 * 3)()
+        _lib.check(L.dtfftb_kernel_dump_table(self._h, int(unit), int(neighbor), 0, None, C.byref(nb), C.byref(total),
+                                              launch), "dtfftb_kernel_dump_table")
+        rows = np.zeros((nb.value, 20), np.int64)
+        if nb.value:
+            _lib.check(L.dtfftb_kernel_dump_table(self._h, int(unit), int(neighbor), nb.value,
+                                                  rows.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nb), C.byref(total),
+                                                  launch), "dtfftb_kernel_dump_table")
+        return {"blocks": rows, "total_items": int(total.value), "launch": [int(v) for v in launch]}
+
     def execute(self, inbuf, outbuf, stream=None, neighbor=None, sync=False):
         """``abstract_kernel%execute`` (src/dtfft_abstract_kernel.F90:290-403). ``neighbor`` is 1-based."""
         _lib.check(_lib.lib().dtfftb_kernel_execute(self._h, _ptr(inbuf), _ptr(outbuf), _stream(stream),

@@ -123,6 +123,27 @@ int dtfftb_kernel_set_tile(dtfftb_kernel_t kernel, int ka, int kb, int rows);
 int dtfftb_kernel_autotune(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
                            int n_iters, float* best_ms);
 
+/* ---- host-only introspection (tests on CPU boxes; nothing here touches a device) ----------
+ * A "dry" kernel builds its geometry and its device tables exactly as a real one but never
+ * uploads or launches them (execute returns DTFFT_ERROR_GPU_NOT_SET).
+ * dtfftb_kernel_create_boxes_dry: kernel over explicit boxes like the plan layer's fused NVLink
+ * path and brick reshapes; `family` 2 = tiled transpose, 3 = row copy; boxes = 10 x n int64
+ * (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2, elements); `remote_peers` != 0 gives box i its
+ * own destination buffer (stand-in for a peer-mapped pointer; turns on the peer interleaving).
+ * dtfftb_kernel_dump_table: the work-item table of one launch -- all peers (`neighbor` = 0) or one
+ * (1-based); `unit` = 4 / 8 / 16 selects the access width of the row-copy family (ignored by the
+ * transpose family).  rows = 20 x cap int64 per block: in_off out_off is1 is2 os0 os1 os2
+ * item_begin shuffle n0 n1 n2 tiles0 tiles1 div0.mul div0.shr div1.mul div1.shr dest reserved
+ * (offsets / strides in `unit`s for the row-copy family, in elements for the transpose family;
+ * dest = index of the destination buffer or -1 for the launch's `out`).  launch[3] = (KA, KB, ROWS)
+ * of transpose_tiles_kernel or (TX, TY, rows per thread) of rows_copy_kernel. */
+int dtfftb_kernel_create_dry(dtfftb_kernel_t* kernel, int ndims, const int32_t* dims, int kernel_type,
+                             int64_t base_storage, const int32_t* neighbor_data, int n_neighbors);
+int dtfftb_kernel_create_boxes_dry(dtfftb_kernel_t* kernel, int family, int64_t base_storage, int n_boxes,
+                                   const int64_t* boxes, int remote_peers);
+int dtfftb_kernel_dump_table(dtfftb_kernel_t kernel, int unit, int neighbor, int32_t cap, int64_t* rows,
+                             int32_t* n_blocks, int64_t* total_items, int32_t* launch);
+
 /* ------------------------------------------------------------------------------------
  * Exchange-backend plugin surface -- replaces backend_nccl (src/dtfft_backend_nccl.F90:38-134)
  * behind the deferred interface of abstract_backend (create_private / execute_private /
