@@ -215,3 +215,27 @@ def test_brick_reshape_tables(cuts):
                 assert ran >= 1
                 k.destroy()
     Config()._commit()
+
+
+def _random_kernel_cases(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_cases):
+        nd_ = int(rng.choice([2, 3]))
+        hi = 70 if nd_ == 3 else 300
+        dims = [int(v) for v in rng.integers(1, hi, size=nd_)]
+        out.append((dims, int(rng.choice([4, 8, 16])), int(rng.choice([0, 7, 64, 1000]))))
+    return out
+
+
+@pytest.mark.parametrize("dims,es,grid", _random_kernel_cases(30, 99))
+def test_random_permute_tables(dims, es, grid):
+    """Random shapes (extents of 1, primes, smaller than a tile) and grid sizes: one CTA per item or a
+    grid-stride loop must give the same, exact result."""
+    n = int(np.prod(dims))
+    src = _rand(n, es, seed=n)
+    kinds = [K.KERNEL_PERMUTE_FORWARD, K.KERNEL_PERMUTE_BACKWARD] + ([K.KERNEL_PERMUTE_BACKWARD_START] if len(dims) == 3 else [])
+    for kt in kinds:
+        k = Kernel().create_dry(dims, es, kt)
+        _check(k, es, kt, dims, src, n, None, 0, grid=grid or None)
+        k.destroy()
