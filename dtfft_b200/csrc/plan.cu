@@ -1075,6 +1075,14 @@ int Plan::mem_alloc(size_t bytes, void** ptr) {
     *ptr = nullptr;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (bytes == 0) return DTFFT_ERROR_INVALID_ALLOC_BYTES;
+    {  // reshape_plan_base.F90:412, 429-432: refuse what cannot fit instead of letting the allocator fail
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            if (bytes > free_b) return DTFFT_ERROR_ALLOC_FAILED;
+        } else {
+            cudaGetLastError();
+        }
+    }
     Alloc a{};
     a.bytes = bytes;
     const bool fused = backend_ == BACKEND_NVLINK_FUSED || reshape_backend_ == BACKEND_NVLINK_FUSED;

@@ -106,6 +106,9 @@ static void transpose_only_3d() {
     CUDA_OK(cudaStreamSynchronize(stream));
     EXPECT(plan.mem_free(a) == Error::SUCCESS && plan.mem_free(b) == Error::SUCCESS && plan.mem_free(c) == Error::SUCCESS);
     EXPECT(plan.mem_free(c) == Error::FREE_FAILED);
+    void* huge = nullptr;  // more than the device has: refused up front (reshape_plan_base.F90:429-432)
+    EXPECT(plan.mem_alloc((size_t)1 << 50, &huge) == Error::ALLOC_FAILED && huge == nullptr);
+    EXPECT(plan.mem_alloc(0, &huge) == Error::INVALID_ALLOC_BYTES);
     EXPECT(plan.destroy() == Error::SUCCESS && plan.c_struct() == nullptr);
     EXPECT(plan.get_alloc_size(nullptr) == Error::PLAN_NOT_CREATED);
 }
