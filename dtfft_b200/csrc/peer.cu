@@ -265,11 +265,9 @@ void* PeerRegistry::peer_ptr(int r, int slot, size_t offset) const {
     return (char*)slots_[(size_t)slot].mapped[(size_t)r] + offset;
 }
 
-int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStream_t stream) {
-    if (!available_) return DTFFTB_ERROR_INTERNAL;
+PeerRegistry::Group* PeerRegistry::group_for(const std::vector<int>& members, int channel, int* rc) {
+    *rc = DTFFT_SUCCESS;
     const int n = (int)members.size();
-    if (n <= 1) return DTFFT_SUCCESS;
-    if (channel < 0 || channel >= kChannels || n > 1024) return DTFFTB_ERROR_INTERNAL;
     auto key = std::make_pair(channel, members);
     auto it = groups_.find(key);
     if (it == groups_.end()) {
@@ -278,17 +276,74 @@ int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStre
         std::vector<uint64_t*> bases((size_t)n);
         for (int t = 0; t < n; ++t) bases[(size_t)t] = (uint64_t*)peer_ptr(members[(size_t)t], flags_slot_, 0);
         cudaError_t ce = cudaMalloc(&g.d_peer_flags, n * sizeof(uint64_t*));
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaMalloc(&g.d_members, n * sizeof(int));
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaMalloc(&g.d_epoch, sizeof(uint64_t));
-        if (ce != cudaSuccess) return cuda_error(ce);
+        if (ce == cudaSuccess) ce = cudaMalloc(&g.d_members, n * sizeof(int));
+        if (ce == cudaSuccess) ce = cudaMalloc(&g.d_epoch, sizeof(uint64_t));
+        if (ce != cudaSuccess) {
+            *rc = cuda_error(ce);
+            return nullptr;
+        }
         cudaMemset(g.d_epoch, 0, sizeof(uint64_t));
         cudaMemcpy(g.d_peer_flags, bases.data(), n * sizeof(uint64_t*), cudaMemcpyHostToDevice);
         cudaMemcpy(g.d_members, members.data(), n * sizeof(int), cudaMemcpyHostToDevice);
         it = groups_.emplace(key, g).first;
     }
-    Group& g = it->second;
+    return &it->second;
+}
+
+const FusedSync* PeerRegistry::fused_sync(const std::vector<int>& members, int channel_free, int channel_landed) {
+    if (!available_ || !flags_) return nullptr;
+    const int n = (int)members.size();
+    if (n <= 1 || n > 128) return nullptr;
+    if (channel_free < 0 || channel_free >= kChannels || channel_landed < 0 || channel_landed >= kChannels) return nullptr;
+    auto key = std::make_pair(channel_free, members);
+    auto it = syncs_.find(key);
+    if (it != syncs_.end()) return it->second.d_state;
+    int rc = 0;
+    Group* gf = group_for(members, channel_free, &rc);
+    if (!gf) return nullptr;
+    Group* gl = group_for(members, channel_landed, &rc);
+    if (!gl) return nullptr;
+    const int P = world_.size();
+    SyncEntry e;
+    if (cudaMalloc(&e.d_state, sizeof(FusedSync)) != cudaSuccess || cudaMalloc(&e.d_tickets, 2 * sizeof(unsigned int)) != cudaSuccess) {
+        cudaGetLastError();
+        if (e.d_state) cudaFree(e.d_state);
+        return nullptr;
+    }
+    cudaMemset(e.d_tickets, 0, 2 * sizeof(unsigned int));
+    FusedSync h{};
+    h.peer_flags = reinterpret_cast<unsigned long long* const*>(gf->d_peer_flags);
+    h.my_flags = reinterpret_cast<unsigned long long*>(flags_);
+    h.members = gf->d_members;
+    h.n = n, h.me = world_.rank();
+    h.row_free = (long long)channel_free * P, h.row_landed = (long long)channel_landed * P;
+    h.epoch_free = reinterpret_cast<unsigned long long*>(gf->d_epoch);
+    h.epoch_landed = reinterpret_cast<unsigned long long*>(gl->d_epoch);
+    h.tickets = e.d_tickets;
+    h.err = reinterpret_cast<unsigned long long*>(flags_ + (size_t)kChannels * P);
+    h.timeout_cycles = 40ll * 1000 * 1000 * 1000;  // as barrier(): ~20 s, then a sticky error instead of a hung GPU
+    cudaMemcpy(e.d_state, &h, sizeof(h), cudaMemcpyHostToDevice);
+    syncs_.emplace(key, e);
+    return e.d_state;
+}
+
+void PeerRegistry::free_syncs() {
+    for (auto& kv : syncs_) {
+        if (kv.second.d_state) cudaFree(kv.second.d_state);
+        if (kv.second.d_tickets) cudaFree(kv.second.d_tickets);
+    }
+    syncs_.clear();
+}
+
+int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStream_t stream) {
+    if (!available_) return DTFFTB_ERROR_INTERNAL;
+    const int n = (int)members.size();
+    if (n <= 1) return DTFFT_SUCCESS;
+    if (channel < 0 || channel >= kChannels || n > 1024) return DTFFTB_ERROR_INTERNAL;
+    int grc = 0;
+    Group* gp = group_for(members, channel, &grc);
+    if (!gp) return grc;
+    Group& g = *gp;
     const int P = world_.size();
     uint64_t* err = flags_ + (size_t)kChannels * P;
     // ~20 s at 2 GHz: a missing peer turns into a sticky error instead of a hung GPU
@@ -305,6 +360,7 @@ int PeerRegistry::reset_barriers() {
     cudaError_t ce = cudaDeviceSynchronize();  // my barriers have completed ...
     if (ce != cudaSuccess) return cuda_error(ce);
     world_.barrier();                          // ... and so have everybody's: nobody reads or writes flags now
+    free_syncs();
     for (auto& kv : groups_) {
         if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
         if (kv.second.d_members) cudaFree(kv.second.d_members);
@@ -328,6 +384,7 @@ int PeerRegistry::error_state() {
 
 void PeerRegistry::destroy() {
     if (!inited_) return;
+    free_syncs();
     for (auto& kv : groups_) {
         if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
         if (kv.second.d_members) cudaFree(kv.second.d_members);

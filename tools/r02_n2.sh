@@ -8,3 +8,6 @@ for s in 1 0; do DTFFTB_RESHAPE_SHORTCUTS=$s timeout 300 $TR --master-port 2952$
 for g in 0 1; do DTFFTB_GRAPHS_NCCL=$g timeout 300 $TR --master-port 2953$g tools/configs_bench.py --configs c2fft,c4 --backends nccl,nccl_pipe --overlap 1 --scale 0.5 > gpurun_out/r02a_half_ncclgraphs${g}_n2.jsonl 2> gpurun_out/r02a_half_ncclgraphs${g}_n2.err; cut -c 1-330 gpurun_out/r02a_half_ncclgraphs${g}_n2.jsonl; tail -3 gpurun_out/r02a_half_ncclgraphs${g}_n2.err; done
 # 4. the bench line
 timeout 300 $TR --master-port 29540 bench.py --gpus 2 > gpurun_out/r02a_bench_n2.json 2> gpurun_out/r02a_bench_n2.err; cut -c 1-600 gpurun_out/r02a_bench_n2.json; tail -3 gpurun_out/r02a_bench_n2.err
+# 5. barriers folded into the fused kernel (opt-in, first run ever: keep it under its own timeout): parity, then A/B
+DTFFTB_FUSED_SYNC=1 DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 300 $TR --master-port 29541 tests/_gpu_worker.py 2>&1 | tail -5
+DTFFTB_FUSED_SYNC=1 timeout 300 $TR --master-port 29542 bench.py --gpus 2 > gpurun_out/r02a_bench_n2_fusedsync.json 2> gpurun_out/r02a_bench_n2_fusedsync.err; cut -c 1-600 gpurun_out/r02a_bench_n2_fusedsync.json; tail -3 gpurun_out/r02a_bench_n2_fusedsync.err

@@ -5,3 +5,5 @@ DTFFTB_LOG=1 timeout 300 $TR --master-port 29551 tools/grid_search_probe.py > gp
 # 2. multi-GPU suite (fused backend only keeps it short) and the bench line
 DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -15
 timeout 300 $TR --master-port 29552 bench.py --gpus 8 > gpurun_out/r02a_bench_n8.json 2> gpurun_out/r02a_bench_n8.err; cut -c 1-700 gpurun_out/r02a_bench_n8.json; tail -3 gpurun_out/r02a_bench_n8.err
+# 3. (only if the 2-GPU run of DTFFTB_FUSED_SYNC=1 was green) the exchange transposition with folded barriers
+DTFFTB_FUSED_SYNC=1 timeout 300 $TR --master-port 29553 bench.py --gpus 8 > gpurun_out/r02a_bench_n8_fusedsync.json 2> gpurun_out/r02a_bench_n8_fusedsync.err; cut -c 1-700 gpurun_out/r02a_bench_n8_fusedsync.json; tail -3 gpurun_out/r02a_bench_n8_fusedsync.err
