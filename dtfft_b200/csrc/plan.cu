@@ -265,6 +265,10 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
         if (reshape_backend_ == BACKEND_NVLINK_FUSED && !peers_.available()) reshape_backend_ = BACKEND_NCCL;
     }
     if (is_reshape_enabled_) {
+        if (P > 1 && effort_ >= DTFFT_EXHAUSTIVE && cfg_.reshape_backend == BACKEND_NONE) {
+            rc = autotune_reshape_backend();
+            if (rc) return rc;
+        }
         rc = build_reshape_handles(reshape_backend_);
         if (rc) return rc;
     }
@@ -681,7 +685,9 @@ int Plan::build_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle
     return DTFFT_SUCCESS;
 }
 
-int Plan::build_reshape_handles(int backend) {
+int Plan::build_reshape_handles(int backend) { return build_reshape_handles(backend, rhandles_); }
+
+int Plan::build_reshape_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& rhandles_) {
     rhandles_.clear();
     HandleContext ctx;
     ctx.nccl = nccl_;
@@ -734,18 +740,19 @@ int Plan::describe_reshape(int rtype, std::vector<int>* members, int* me, Reshap
     return DTFFT_SUCCESS;
 }
 
-int Plan::time_backend(int backend, double* ms) {
-    // execute_autotune, src/dtfft_reshape_plan_base.F90:588-706: every transposition once per
-    // iteration, warm-up + timed iterations, result = max over ranks of the mean
+int Plan::time_backend(int backend, double* ms, bool reshapes) {
+    // execute_autotune, src/dtfft_reshape_plan_base.F90:588-706: every transposition (or every
+    // reshape) once per iteration, warm-up + timed iterations, result = max over ranks of the mean
     std::map<int, std::unique_ptr<ReshapeHandle>> hs;
-    int rc = build_handles(backend, hs);
+    int rc = reshapes ? build_reshape_handles(backend, hs) : build_handles(backend, hs);
     *ms = 1e30;
     int ok = rc == DTFFT_SUCCESS;
     if (comm_.sum(ok) != comm_.size()) return DTFFT_SUCCESS;  // backend unusable somewhere: skip it
     size_t bytes = alloc_bytes(), aux = 0;
     for (auto& kv : hs) aux = std::max(aux, (size_t)kv.second->aux_bytes());
-    const int saved = backend_;
+    const int saved = backend_, saved_r = reshape_backend_;
     backend_ = backend;  // mem_alloc picks the allocator by backend
+    if (reshapes) reshape_backend_ = backend;
     void *a = nullptr, *b = nullptr, *w = nullptr;
     rc = mem_alloc(bytes, &a);
     if (!rc) rc = mem_alloc(bytes, &b);
@@ -781,6 +788,7 @@ int Plan::time_backend(int backend, double* ms) {
     if (b) mem_free(b);
     if (a) mem_free(a);
     backend_ = saved;
+    reshape_backend_ = saved_r;
     return rc;
 }
 
@@ -836,6 +844,24 @@ int Plan::autotune_grid(bool all_backends) {
     backend_ = best_b;
     log("DTFFT_MEASURE: selected process grid 1x%dx%d", best1, best2);
     if (all_backends) log("DTFFT_PATIENT: selected backend is %s", dtfft_get_backend_string((dtfft_backend_t)backend_));
+    return DTFFT_SUCCESS;
+}
+
+int Plan::autotune_reshape_backend() {
+    // autotune_reshape_plan (src/dtfft_reshape_plan.F90:206-222, 487-560): the four reshapes timed
+    // with every enabled backend, the fastest kept
+    const std::vector<int> cands = backend_candidates();
+    double best = 1e30;
+    int best_b = reshape_backend_;
+    for (int b : cands) {
+        double ms = 1e30;
+        int rc = time_backend(b, &ms, true);
+        if (rc) return rc;
+        log("autotune reshape backend %s: %.4f ms", dtfft_get_backend_string((dtfft_backend_t)b), ms);
+        if (ms < best) best = ms, best_b = b;
+    }
+    reshape_backend_ = best_b;
+    log("DTFFT_EXHAUSTIVE: selected reshape backend is %s", dtfft_get_backend_string((dtfft_backend_t)reshape_backend_));
     return DTFFT_SUCCESS;
 }
 

@@ -171,14 +171,16 @@ private:
     int init_nccl();
     int build_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& into);
     int build_reshape_handles(int backend);
+    int build_reshape_handles(int backend, std::map<int, std::unique_ptr<ReshapeHandle>>& into);
     int autotune_backend();
+    int autotune_reshape_backend();  // DTFFT_EXHAUSTIVE, src/dtfft_reshape_plan.F90:206-222
     // DTFFT_MEASURE / DTFFT_PATIENT process-grid search (autotune_grid_decomposition,
     // src/dtfft_transpose_plan.F90:391-540); `all_backends` also times every enabled backend per grid.
     int autotune_grid(bool all_backends);
     void set_grid(int g1, int g2);
     std::vector<int> backend_candidates() const;
     int choose_overlap();
-    int time_backend(int backend, double* ms);
+    int time_backend(int backend, double* ms, bool reshapes = false);
     int create_ffts();
     int check_aux(void* aux, bool from_execute, void** aux1, void** aux2);
     int check_device_ptrs(const void* a, const void* b, const void* c) const;

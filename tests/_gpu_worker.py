@@ -229,6 +229,28 @@ def main():
     plan.mem_free(bb)
     plan.destroy()
 
+    # DTFFT_EXHAUSTIVE on a brick plan: timed choice of the reshape backend too (autotune_reshape_plan,
+    # src/dtfft_reshape_plan.F90:206-222), then a correct reshape
+    picked_r = None
+    if world % 2 == 0:
+        plan = PlanR2R(Pencil(*boxes[rank]), comm=comm, effort=Effort.EXHAUSTIVE,
+                       config=Config(enable_z_slab=False, enable_fourier_reshape=True))
+        picked_r = plan.reshape_backend
+        assert picked_r in (Backend.NCCL, Backend.NCCL_PIPELINED, Backend.NVLINK_FUSED)
+        G = P.global_array(plan.dims, np.float64, kind="index")
+        b1 = oracle_pencil(plan.get_pencil(Layout.X_BRICKS))
+        xp = oracle_pencil(plan.get_pencil(Layout.X_PENCILS))
+        src, want = P.pencil_slice(G, b1), P.pencil_slice(G, xp)
+        ab, at = dev_buf(plan, plan.alloc_bytes, src)
+        bb, bt = dev_buf(plan, plan.alloc_bytes)
+        dist.barrier()
+        plan.reshape(at, bt, Reshape.X_BRICKS_TO_PENCILS)
+        sync(plan)
+        assert np.array_equal(host(bt, np.float64, want.size), want), ("EXHAUSTIVE reshape", rank)
+        plan.mem_free(ab)
+        plan.mem_free(bb)
+        plan.destroy()
+
     # DTFFT_MEASURE on an FFT plan with the NVLINK_FUSED backend: timed choice of the stage overlap
     # (choose_overlap), then a forward + backward round trip within the reference's tolerance
     dims = [128, 64, 96]
@@ -253,7 +275,7 @@ def main():
     plan.destroy()
     Config()._commit()
     dist.barrier()
-    print(f"rank {rank}/{world}: multi-GPU plan checks OK ({checked} cases, PATIENT picked {picked.name}, MEASURE overlap {tuned})", flush=True)
+    print(f"rank {rank}/{world}: multi-GPU plan checks OK ({checked} cases, PATIENT picked {picked.name}, EXHAUSTIVE reshape backend {picked_r.name if picked_r else '-'}, MEASURE overlap {tuned})", flush=True)
     dist.destroy_process_group()
 
 
