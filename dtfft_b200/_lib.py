@@ -133,6 +133,8 @@ def _declare_plan_api(L):
         "dtfftb_plan_create_dry": [C.c_int, C.c_int8, i32p, vp, vp, C.c_int, C.c_int, pvp],
         "dtfftb_plan_describe_exchange": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, i32p, i32p, i32p,
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
+        "dtfftb_plan_describe_chunk": [vp, C.c_int, C.c_int32, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_reshape": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
     }

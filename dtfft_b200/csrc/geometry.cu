@@ -381,6 +381,28 @@ RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankL
     return s;
 }
 
+std::vector<Box> chunk_boxes(const Pencil& send, const std::vector<Pencil>& recv_by_member, int k, int nchunks,
+                             long long* chunk_offset) {
+    const int P = (int)recv_by_member.size();
+    const int nd = send.ndims;
+    const long long n = nd > 0 ? send.counts[nd - 1] : 1;
+    const long long lo = n * k / nchunks, hi = n * (k + 1) / nchunks;
+    long long slow_stride = 1;  // elements per index of the slowest axis
+    for (int j = 0; j + 1 < nd; ++j) slow_stride *= send.counts[j];
+    if (chunk_offset) *chunk_offset = lo * slow_stride;
+    // the chunk as a layout of its own: same axes, the slowest one restricted to [lo, hi)
+    Pencil part = send;
+    part.starts[nd - 1] += (int32_t)lo;
+    part.counts[nd - 1] = (int32_t)(hi - lo);
+    const RankLayout src = layout_of(part);
+    std::vector<Box> boxes((size_t)P);
+    for (int i = 0; i < P; ++i) {
+        bool tr = false;
+        boxes[(size_t)i] = hi > lo ? intersect_box(src, layout_of(recv_by_member[(size_t)i]), &tr) : Box{};
+    }
+    return boxes;
+}
+
 namespace {
 // pack / unpack boxes and exchange tables of member `m`
 void reshape_tables(const std::vector<Pencil>& send_by_member, const std::vector<Pencil>& recv_by_member, int m,

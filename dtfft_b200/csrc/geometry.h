@@ -119,6 +119,12 @@ Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposin
 // the intersection, stored in the axis order of `order_like`.
 RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like);
 
+// Stage overlap of the fused path: chunk k of n along the SLOWEST axis of the source pencil, as a
+// transposition of its own.  boxes[i] = part of the chunk owned by member i afterwards, with in_off
+// relative to the chunk's first element (returned in *chunk_offset, elements of the full pencil).
+std::vector<Box> chunk_boxes(const Pencil& send, const std::vector<Pencil>& recv_by_member, int k, int nchunks,
+                             long long* chunk_offset);
+
 // ---- brick <-> pencil reshape over NCCL: pack -> all-to-all(v) -> unpack -------------------
 // Block (me -> i) is the global-index intersection of my source with i's destination, carried
 // in a contiguous slot in DESTINATION axis order (both sides of a reshape share the axis order,

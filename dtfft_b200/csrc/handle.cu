@@ -218,9 +218,6 @@ int ReshapeHandle::fused_end(cudaStream_t stream) {
 
 int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_ctas, cudaStream_t stream) {
     if (!can_chunk() || k < 0 || k >= nchunks) return DTFFTB_ERROR_INTERNAL;
-    const int P = (int)members_.size();
-    const int nd = send_.ndims;
-    const long long n = slow_extent();
     auto key = std::make_pair((const void*)out, nchunks);
     auto it = fused_chunks_.find(key);
     if (it == fused_chunks_.end()) {
@@ -229,17 +226,7 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
         if (rc) return rc;
         std::vector<std::unique_ptr<Kernel>> ks((size_t)nchunks);
         for (int c = 0; c < nchunks; ++c) {
-            const long long lo = n * c / nchunks, hi = n * (c + 1) / nchunks;
-            // the chunk as a layout of its own: same axes, the slowest one restricted to [lo, hi)
-            Pencil part = send_;
-            part.starts[nd - 1] += (int32_t)lo;
-            part.counts[nd - 1] = (int32_t)(hi - lo);
-            const RankLayout src = layout_of(part);
-            std::vector<Box> boxes((size_t)P);
-            for (int i = 0; i < P; ++i) {
-                bool tr = false;
-                boxes[(size_t)i] = hi > lo ? intersect_box(src, layout_of(recv_by_member_[(size_t)i]), &tr) : Box{};
-            }
+            const std::vector<Box> boxes = chunk_boxes(send_, recv_by_member_, c, nchunks, nullptr);
             ks[(size_t)c].reset(new Kernel);
             rc = ks[(size_t)c]->create_boxes(fused_family_, es_, boxes);
             if (rc) return rc;
@@ -251,10 +238,9 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
     }
     Kernel& kern = *it->second[(size_t)k];
     kern.set_grid_limit(max_ctas);
-    long long slow_stride = 1;  // elements per index of the slowest axis
-    for (int j = 0; j + 1 < nd; ++j) slow_stride *= send_.counts[j];
-    const long long lo = n * k / nchunks;
-    return kern.execute_all(static_cast<char*>(in) + (size_t)(lo * slow_stride) * (size_t)es_, out, stream);
+    long long chunk_offset = 0;  // first element of chunk k in the source pencil
+    chunk_boxes(send_, recv_by_member_, k, nchunks, &chunk_offset);
+    return kern.execute_all(static_cast<char*>(in) + (size_t)chunk_offset * (size_t)es_, out, stream);
 }
 
 int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {

@@ -740,6 +740,18 @@ int Plan::describe_reshape(int rtype, std::vector<int>* members, int* me, Reshap
     return DTFFT_SUCCESS;
 }
 
+int Plan::describe_chunk(int ttype, int k, int nchunks, std::vector<int>* members, std::vector<Box>* boxes,
+                         long long* chunk_offset) const {
+    if (std::abs(ttype) < 1 || std::abs(ttype) > 3) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+    if (nchunks < 1 || k < 0 || k >= nchunks) return DTFFT_ERROR_INVALID_USAGE;
+    HandleSpec hs;
+    int rc = handle_spec(ttype, &hs);
+    if (rc) return rc;
+    if (members) *members = hs.members;
+    *boxes = chunk_boxes(hs.send[(size_t)hs.me], hs.recv, k, nchunks, chunk_offset);
+    return DTFFT_SUCCESS;
+}
+
 int Plan::time_backend(int backend, double* ms, bool reshapes) {
     // execute_autotune, src/dtfft_reshape_plan_base.F90:588-706: every transposition (or every
     // reshape) once per iteration, warm-up + timed iterations, result = max over ranks of the mean

@@ -152,6 +152,9 @@ public:
     // Brick <-> pencil reshape over the NCCL backends: pack / unpack boxes, exchange tables and
     // the pack-free / unpack-free flags (geometry.h: reshape_geometry).
     int describe_reshape(int rtype, std::vector<int>* members, int* me, ReshapeGeometry* g) const;
+    // Boxes of chunk k of n of the stage-overlapped fused transposition `ttype` (geometry.h: chunk_boxes).
+    int describe_chunk(int ttype, int k, int nchunks, std::vector<int>* members, std::vector<Box>* boxes,
+                       long long* chunk_offset) const;
     std::vector<int> transpose_types() const;
 
 private:

@@ -647,6 +647,27 @@ dtfft_error_t dtfftb_plan_describe_reshape(dtfft_plan_t plan, int reshape_type, 
     return DTFFT_SUCCESS;
 }
 
+dtfft_error_t dtfftb_plan_describe_chunk(dtfft_plan_t plan, int transpose_type, int32_t k, int32_t nchunks, int32_t cap,
+                                         int32_t* n_members, int64_t* boxes, int64_t* chunk_offset) {
+    PLAN_OR_RETURN(plan);
+    if (!n_members) return DTFFT_ERROR_INVALID_USAGE;
+    std::vector<int> mem;
+    std::vector<dtfftb::Box> bx;
+    long long off = 0;
+    int rc = P(plan)->describe_chunk(transpose_type, k, nchunks, &mem, &bx, &off);
+    if (rc) return E(rc);
+    *n_members = (int32_t)mem.size();
+    if (chunk_offset) *chunk_offset = off;
+    if (!boxes || (int)mem.size() > cap) return DTFFT_SUCCESS;
+    for (size_t i = 0; i < bx.size(); ++i) {
+        const dtfftb::Box& b = bx[i];
+        int64_t* o = boxes + 10 * i;
+        o[0] = b.empty() ? 0 : b.n0, o[1] = b.n1, o[2] = b.n2, o[3] = b.in_off, o[4] = b.out_off;
+        o[5] = b.is1, o[6] = b.is2, o[7] = b.os0, o[8] = b.os1, o[9] = b.os2;
+    }
+    return DTFFT_SUCCESS;
+}
+
 int dtfftb_plan_peer_error(dtfft_plan_t plan) {
     if (!plan) return 0;
     return P(plan)->peer_error();

@@ -593,6 +593,20 @@ class Plan:
                 "send_displs": cd[1], "recv_counts": cd[2], "recv_displs": cd[3], "fused_boxes": boxes,
                 "fused_transposing": bool(tr.value)}
 
+    def describe_chunk(self, transpose_type, k: int, nchunks: int) -> dict:
+        """Boxes of chunk ``k`` of ``nchunks`` of a stage-overlapped fused transposition (dtfftb_plan_describe_chunk)."""
+        import numpy as np
+
+        L = _lib.lib()
+        n, off = C.c_int32(0), C.c_int64(0)
+        _check(L.dtfftb_plan_describe_chunk(self._h, int(transpose_type), int(k), int(nchunks), 0, C.byref(n), None,
+                                            C.byref(off)), "dtfftb_plan_describe_chunk")
+        boxes = np.zeros((n.value, 10), np.int64)
+        _check(L.dtfftb_plan_describe_chunk(self._h, int(transpose_type), int(k), int(nchunks), n.value, C.byref(n),
+                                            boxes.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(off)),
+               "dtfftb_plan_describe_chunk")
+        return {"boxes": boxes, "chunk_offset": int(off.value)}
+
     def describe_reshape(self, type_) -> dict:
         """NCCL-path geometry of one brick <-> pencil reshape on this rank (dtfftb_plan_describe_reshape)."""
         import numpy as np

@@ -355,6 +355,12 @@ dtfft_error_t dtfftb_plan_describe_exchange(dtfft_plan_t plan, int type, int32_t
 dtfft_error_t dtfftb_plan_describe_reshape(dtfft_plan_t plan, int reshape_type, int32_t cap, int32_t* n_members,
                                            int32_t* my_index, int32_t* members, int64_t* pack_boxes,
                                            int64_t* unpack_boxes, int64_t* counts_displs, int32_t* flags);
+/* Stage overlap of the cuFFT executor with the NVLINK_FUSED exchange: chunk `k` of `nchunks` (cut along the
+ * slowest axis of the source pencil) of transposition `transpose_type` as a transposition of its own.
+ * boxes = 10 x P int64 (layout as fused_boxes, in_off relative to the chunk), *chunk_offset = first element
+ * of the chunk in the source pencil.  Works on dry and real plans. */
+dtfft_error_t dtfftb_plan_describe_chunk(dtfft_plan_t plan, int transpose_type, int32_t k, int32_t nchunks, int32_t cap,
+                                         int32_t* n_members, int64_t* boxes, int64_t* chunk_offset);
 
 #ifdef __cplusplus
 }

@@ -121,6 +121,38 @@ def test_fused_boxes_reproduce_datatype_path(dims, nranks):
             assert np.array_equal(got[r], want[r]), (L.TRANSPOSE_NAMES[t], r)
 
 
+@pytest.mark.parametrize("dims,nranks,nchunks", [((48, 21, 36), 6, 3), ((40, 33, 28), 4, 8), ((37, 22), 3, 4),
+                                                 ((64, 20, 18), 8, 5), ((16, 12, 5), 2, 8)])
+def test_stage_overlap_chunks_tile_the_transposition(dims, nranks, nchunks):
+    """Stage overlap of the FFT with the fused exchange (Plan::run_fft_transpose): the source pencil is cut
+    along its slowest axis; the boxes of chunk k (dtfftb_plan_describe_chunk), applied to the chunk's part
+    of the source, must together deliver exactly the destination pencils of the whole transposition --
+    also when there are more chunks than planes (empty chunks) or the cut is uneven."""
+    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=Config(enable_z_slab=False), dry=True))
+    comm_dims = plans[0].grid_dims
+    nd = len(dims)
+    G = P.global_array(dims, np.complex128, kind="index")
+    for t in ([1, -1] if nd == 2 else [1, -1, 2, -2]):
+        src = P.scatter_input(G, list(dims), comm_dims, t)
+        want = P.transpose_datatype(G, list(dims), comm_dims, t)
+        dsts = [np.full(w.size, -7, np.complex128) for w in want]
+        hits = [np.zeros(w.size, np.int32) for w in want]
+        for r, plan in enumerate(plans):
+            members = plan.describe_exchange(t)["members"]
+            covered = 0
+            for k in range(nchunks):
+                d = plan.describe_chunk(t, k, nchunks)
+                part = src[r][d["chunk_offset"]:]
+                P.apply_boxes(part, dsts, d["boxes"], members)
+                P.apply_boxes(np.ones(part.size, np.int32), hits, d["boxes"], members)  # overwrites: counted below
+                covered += int(sum(b[0] * b[1] * b[2] for b in d["boxes"] if b[0] > 0))
+            assert covered == src[r].size, (t, r)  # every source element belongs to exactly one chunk box
+        for r in range(nranks):
+            assert np.array_equal(dsts[r], want[r]), (L.TRANSPOSE_NAMES[t], r)
+            assert np.all(hits[r] == 1)
+    Config()._commit()
+
+
 # ---------------------------------------------------------------------------------------------
 # user pencils and bricks
 # ---------------------------------------------------------------------------------------------
