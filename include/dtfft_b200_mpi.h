@@ -1,6 +1,6 @@
 /*
- * dtfft_b200_mpi.h -- header-only adapter for MPI programs (not compiled in this repository:
- * the build image has no MPI).  Turns an MPI_Comm into the dtfftb_comm_t the library takes in
+ * dtfft_b200_mpi.h -- header-only adapter for MPI programs (the build image has no MPI: the header
+ * is compiled and exercised against a single-process stand-in, tests/c/mpi_stub/mpi.h).  Turns an MPI_Comm into the dtfftb_comm_t the library takes in
  * place of the reference's `MPI_Comm comm` argument (include/dtfft.h:397-515 of the reference):
  *
  *     dtfftb_mpi_comm_t c;

@@ -45,6 +45,20 @@ def test_c_host_program():
     assert out.returncode == 0 and "api_host OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
+def test_mpi_adapter_header():
+    """include/dtfft_b200_mpi.h (MPI_Comm -> dtfftb_comm_t) builds warning-free and works, against a
+    single-process stand-in for <mpi.h> (the image has no MPI)."""
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "api_mpi_adapter")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(SRC, "mpi_stub"),
+           "-I" + os.path.join(ROOT, "include"), os.path.join(SRC, "api_mpi_adapter.c"), "-o", exe, "-L" + LIBDIR,
+           "-ldtfft_b200"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=_env(), timeout=300)
+    assert out.returncode == 0, out.stderr[-4000:]
+    out = subprocess.run([exe], capture_output=True, text=True, env=_env(), timeout=120)
+    assert out.returncode == 0 and "api_mpi_adapter OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_fastdiv_host_program():
     """The work-item decoder's division by run-time constants is exact over its whole domain."""
     os.makedirs(OUT, exist_ok=True)
