@@ -680,7 +680,8 @@ int Kernel::autotune(const void* in, void* out, cudaStream_t stream, int n_warmu
     if (best_ms) *best_ms = 0.f;
     if (!created_) return DTFFTB_ERROR_INTERNAL;
     if (noop_ || family_ != FAM_T) return DTFFT_SUCCESS;
-    static const TileCfg cands[] = {{1, 1, 4}, {1, 1, 8}, {1, 1, 16}, {2, 1, 8}, {1, 2, 8}, {2, 2, 8}, {2, 2, 16}};
+    static const TileCfg cands[] = {{1, 1, 4}, {1, 1, 8}, {1, 1, 16}, {2, 1, 8}, {1, 2, 8},
+                                    {2, 2, 8}, {2, 2, 16}, {1, 4, 16}, {4, 1, 16}};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);

@@ -298,6 +298,8 @@ cudaError_t dispatch_T(TileCfg c, const void* in, void* out, const BlockDesc* b,
     DTFFTB_T_CASE(1, 2, 8)
     DTFFTB_T_CASE(2, 2, 8)
     DTFFTB_T_CASE(2, 2, 16)
+    DTFFTB_T_CASE(1, 4, 16)  // 32 x 128: 2 KB contiguous store runs at 16 B / element (round-2 sweep candidates)
+    DTFFTB_T_CASE(4, 1, 16)  // 128 x 32: 2 KB contiguous load runs
 #undef DTFFTB_T_CASE
     return cudaErrorInvalidValue;
 }
@@ -391,7 +393,7 @@ cudaError_t dispatch_R(int tx, const void* in, void* out, const BlockDesc* b, in
 
 bool transpose_cfg_supported(int es, TileCfg c) {
     if (es != 4 && es != 8 && es != 16) return false;
-    const int ok[][3] = {{1, 1, 4}, {1, 1, 8}, {1, 1, 16}, {2, 1, 8}, {1, 2, 8}, {2, 2, 8}, {2, 2, 16}};
+    const int ok[][3] = {{1, 1, 4}, {1, 1, 8}, {1, 1, 16}, {2, 1, 8}, {1, 2, 8}, {2, 2, 8}, {2, 2, 16}, {1, 4, 16}, {4, 1, 16}};
     for (auto& o : ok)
         if (c.ka == o[0] && c.kb == o[1] && c.rows == o[2]) return true;
     return false;

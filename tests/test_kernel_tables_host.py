@@ -239,3 +239,23 @@ def test_random_permute_tables(dims, es, grid):
         k = Kernel().create_dry(dims, es, kt)
         _check(k, es, kt, dims, src, n, None, 0, grid=grid or None)
         k.destroy()
+
+
+ALL_TILES = [(1, 1, 4), (1, 1, 8), (1, 1, 16), (2, 1, 8), (1, 2, 8), (2, 2, 8), (2, 2, 16), (1, 4, 16), (4, 1, 16)]
+
+
+@pytest.mark.parametrize("tile", ALL_TILES)
+@pytest.mark.parametrize("es", [4, 16])
+def test_every_tile_configuration(tile, es):
+    """Every compiled (KA, KB, ROWS) instantiation of the transpose family -- the candidates of the
+    DTFFT_EXHAUSTIVE kernel autotune (src/dtfft_kernel_device.F90:338-397) -- gets a table that moves
+    the right elements on shapes that do not divide the tile."""
+    for dims in ([70, 45, 3], [33, 130, 2], [129, 31]):
+        n = int(np.prod(dims))
+        src = _rand(n, es, seed=7)
+        for kt in (K.KERNEL_PERMUTE_FORWARD, K.KERNEL_PERMUTE_BACKWARD):
+            k = Kernel().create_dry(dims, es, kt)
+            k.set_tile(*tile)
+            assert k.dump_table(unit=es)["launch"] == list(tile)
+            _check(k, es, kt, dims, src, n, None, 0, grid=61)
+            k.destroy()

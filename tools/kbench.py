@@ -13,7 +13,7 @@ from oracle import ref_kernels as R  # noqa: E402  (A/B baseline only)
 from dtfft_b200.kernel import (KERNEL_PERMUTE_BACKWARD, KERNEL_PERMUTE_BACKWARD_START, KERNEL_PERMUTE_FORWARD,  # noqa: E402
                                KERNEL_UNPACK, KERNEL_PERMUTE_BACKWARD_END, Kernel)
 
-TILES = [(1, 1, 8), (2, 1, 8), (1, 2, 8), (2, 2, 8), (2, 2, 16)]
+TILES = [(1, 1, 8), (2, 1, 8), (1, 2, 8), (2, 2, 8), (2, 2, 16), (1, 4, 16), (4, 1, 16)]
 
 
 def time_ms(fn, warmup=3, iters=10):
