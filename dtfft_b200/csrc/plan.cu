@@ -1538,21 +1538,58 @@ int Plan::execute_generic_reshape(void* in, void* out, bool fwd, void* aux, void
 #undef RUN
 
 int Plan::report() const {
-    // dtfft_plan.F90:1557-1631
+    // dtfft_plan.F90:1556-1631, line for line (WRITE_REPORT: rank 0, prefix "dtFFT: "); the lines after
+    // "Reshape Backend" are additions of this implementation.
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (comm_.rank() != 0) return DTFFT_SUCCESS;
-    printf("**dtFFT plan report (dtfft_b200)**\n");
-    printf("  dimensions      : %d (", ndims_);
-    for (int d = 0; d < ndims_; ++d) printf("%s%d", d ? "x" : "", user_dims_[d]);
-    printf(")\n  plan type       : %s\n", kind_ == PLAN_C2C ? "C2C" : kind_ == PLAN_R2C ? "R2C" : "R2R");
-    printf("  precision       : %s\n", dtfft_get_precision_string((dtfft_precision_t)precision_));
-    printf("  executor        : %s\n", dtfft_get_executor_string((dtfft_executor_t)executor_));
-    printf("  platform        : CUDA (sm_100a kernels)\n");
-    printf("  process grid    : %dx%dx%d%s%s\n", comm_dims_[0], comm_dims_[1], comm_dims_[2], is_z_slab_ ? " (Z-slab)" : "",
-           is_y_slab_ ? " (Y-slab)" : "");
-    printf("  backend         : %s\n", dtfft_get_backend_string((dtfft_backend_t)backend_));
-    if (is_reshape_enabled_) printf("  reshape backend : %s\n", dtfft_get_backend_string((dtfft_backend_t)reshape_backend_));
-    printf("  alloc bytes     : %zu, aux bytes: %zu\n", alloc_bytes(), aux_bytes());
+    auto grid_str = [&](const int32_t* d) {
+        char buf[64];
+        if (ndims_ == 2)
+            snprintf(buf, sizeof buf, "%dx%d", d[0], d[1]);
+        else
+            snprintf(buf, sizeof buf, "%dx%dx%d", d[0], d[1], d[2]);
+        return std::string(buf);
+    };
+    auto line = [](const char* fmt, ...) {
+        va_list ap;
+        va_start(ap, fmt);
+        fputs("dtFFT: ", stdout);
+        vfprintf(stdout, fmt, ap);
+        fputc('\n', stdout);
+        va_end(ap);
+    };
+    line("**Plan report**");
+    line("  dtFFT Version        :  %d.%d.%d", DTFFT_VERSION_MAJOR, DTFFT_VERSION_MINOR, DTFFT_VERSION_PATCH);
+    line("  Number of dimensions :  %d", ndims_);
+    line("  Global dimensions    :  %s", grid_str(user_dims_).c_str());
+    line("  Grid decomposition   :  %s", grid_str(comm_dims_).c_str());
+    if (is_reshape_enabled_) {
+        // init_grid = brick grid; final_grid = (P1, P2 / c, c) resp. (P1 / c, c), c = bricks pooled along the
+        // last axis (src/dtfft_reshape_plan.F90:155-158, 199-204)
+        const int last = ndims_ - 1, c = std::max(1, brick_grid_[last]);
+        int32_t fin[3] = {1, 1, 1};
+        if (ndims_ == 3)
+            fin[0] = comm_dims_[1], fin[1] = comm_dims_[2] / c, fin[2] = c;
+        else
+            fin[0] = comm_dims_[1] / c, fin[1] = c;
+        line("  Initial grid         :  %s", grid_str(brick_grid_).c_str());
+        line("  Final grid           :  %s", grid_str(fin).c_str());
+        line("  Final reshape enabled:  %s", is_final_reshape_enabled_ ? "True" : "False");
+    }
+    line("  Execution platform   :  CUDA");
+    line("  Plan type            :  %s", kind_ == PLAN_C2C ? "Complex-to-Complex" : kind_ == PLAN_R2C ? "Real-to-Complex" : "Real-to-Real");
+    line("  Plan precision       :  %s", dtfft_get_precision_string((dtfft_precision_t)precision_));
+    line("  FFT Executor type    :  %s", dtfft_get_executor_string((dtfft_executor_t)executor_));
+    if (ndims_ == 3) {
+        line("  Z-slab enabled       :  %s", is_z_slab_ ? "True" : "False");
+        line("  Y-slab enabled       :  %s", is_y_slab_ ? "True" : "False");
+    }
+    line("  Backend              :  %s", dtfft_get_backend_string((dtfft_backend_t)backend_));
+    if (is_reshape_enabled_) line("  Reshape Backend      :  %s", dtfft_get_backend_string((dtfft_backend_t)reshape_backend_));
+    line("  Alloc / aux bytes    :  %zu / %zu", alloc_bytes(), aux_bytes());
+    line("  Stage overlap chunks :  %d", overlap_chunks_);
+    line("  CUDA graph replay    :  %s", graphs_usable() ? "True" : "False");
+    line("**End of report**");
     fflush(stdout);
     return DTFFT_SUCCESS;
 }
