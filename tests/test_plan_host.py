@@ -507,3 +507,26 @@ def test_python_api_surface_of_the_reference_module():
     c = _shaped_view(flat, (2, 3, 4), "C")
     assert c.stride() == (12, 4, 1) and c[1, 2, 3] == 23
     assert f.data_ptr() == flat.data_ptr() == c.data_ptr()
+
+
+def test_report_follows_the_reference_format(capfd):
+    """dtfft_report: the reference's lines and labels (src/dtfft_plan.F90:1556-1631), incl. the initial /
+    final grids of a plan created from bricks (src/dtfft_reshape_plan.F90:155-158, 199-204)."""
+    boxes = brick_boxes([[30, 34], [20, 12], [70, 58]])
+    cfg = Config(enable_fourier_reshape=True, enable_z_slab=False)
+    plans = dry_world(len(boxes), lambda r, c: PlanR2R(Pencil(*boxes[r]), comm=c, config=cfg, dry=True))
+    capfd.readouterr()
+    for p in plans:
+        p.report()  # only rank 0 prints
+    out = capfd.readouterr().out.splitlines()
+    assert out[0] == "dtFFT: **Plan report**" and out[-1] == "dtFFT: **End of report**"
+    assert sum(l == "dtFFT: **Plan report**" for l in out) == 1
+    body = {l.split(":", 2)[1].strip(): l.split(":", 2)[2].strip() for l in out[1:-1]}
+    assert body["dtFFT Version"] == "3.2.0" and body["Number of dimensions"] == "3"
+    assert body["Global dimensions"] == "64x32x128" and body["Grid decomposition"] == "1x2x4"
+    assert body["Initial grid"] == "2x2x2" and body["Final grid"] == "2x2x2" and body["Final reshape enabled"] == "True"
+    assert body["Execution platform"] == "CUDA" and body["Plan type"] == "Real-to-Real"
+    assert body["Plan precision"] == "Double" and body["FFT Executor type"] == "None"
+    assert body["Z-slab enabled"] == "False" and body["Y-slab enabled"] == "False"
+    assert body["Backend"] == "NCCL" and body["Reshape Backend"] == "NCCL"
+    Config()._commit()
