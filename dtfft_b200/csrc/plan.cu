@@ -128,6 +128,8 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
         rc = init_nccl();
         if (rc) return rc;
     }
+    if (P > 1 && effort_ >= DTFFT_PATIENT && backend_candidates().empty())
+        return DTFFT_ERROR_BACKENDS_DISABLED;  // reshape_plan_base.F90:139-142
     // grid search applies to default 3-D decompositions only (transpose_plan.F90:230-262)
     bool grid_search = P > 1 && ndims_ == 3 && !has_user_pencil_ && !is_z_slab_ && !is_y_slab_ &&
                        !(comm_.raw() && comm_.raw()->cart_ndims > 0) && effort_ >= DTFFT_MEASURE;
@@ -687,8 +689,10 @@ int Plan::time_backend(int backend, double* ms, bool reshapes) {
 }
 
 std::vector<int> Plan::backend_candidates() const {
-    std::vector<int> cands = {BACKEND_NCCL};
-    if (cfg_.enable_pipelined_backends) cands.push_back(BACKEND_NCCL_PIPELINED);
+    // run_autotune_backend's filter (src/dtfft_transpose_plan.F90:763-781) on the backends that exist here
+    std::vector<int> cands;
+    if (cfg_.enable_nccl_backends) cands.push_back(BACKEND_NCCL);
+    if (cfg_.enable_nccl_backends && cfg_.enable_pipelined_backends) cands.push_back(BACKEND_NCCL_PIPELINED);
     if (cfg_.enable_fused_backends && peers_.available()) cands.push_back(BACKEND_NVLINK_FUSED);
     return cands;
 }
