@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "errors.h"
+#include "trace.h"
 
 namespace dtfftb {
 
@@ -36,6 +37,7 @@ void Plan::log(const char* fmt, ...) const {
 int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_pencil_t* pencil, const int* r2r_kinds,
                  const dtfftb_comm_t* comm, int precision, int effort, int executor, bool dry) {
     if (created_) return DTFFT_ERROR_PLAN_IS_CREATED;
+    TraceRange trace_create("dtfft_create", kColorCreate);
     dry_ = dry;
     // ---- check_create_args, src/dtfft_plan.F90:2107-2219 ----
     cfg_ = effective_config();
@@ -718,6 +720,7 @@ int Plan::dry_set_grid(int g1, int g2) {
 }
 
 int Plan::autotune_grid(bool all_backends) {
+    TraceRange trace("Autotune transpose plan", kColorAutotune);  // transpose_plan.F90:233
     const int saved1 = comm_dims_[1], saved2 = comm_dims_[2];
     const std::vector<std::pair<int, int>> grids = grid_candidates(dims_, comm_.size());
     const std::vector<int> backends = all_backends ? backend_candidates() : std::vector<int>{backend_};
@@ -746,6 +749,7 @@ int Plan::autotune_grid(bool all_backends) {
 }
 
 int Plan::autotune_reshape_backend() {
+    TraceRange trace("Autotune reshape plan", kColorAutotune);  // reshape_plan.F90:209
     // autotune_reshape_plan (src/dtfft_reshape_plan.F90:206-222, 487-560): the four reshapes timed
     // with every enabled backend, the fastest kept
     const std::vector<int> cands = backend_candidates();
@@ -764,6 +768,7 @@ int Plan::autotune_reshape_backend() {
 }
 
 int Plan::autotune_backend() {
+    TraceRange trace("Autotune transpose plan", kColorAutotune);
     const std::vector<int> cands = backend_candidates();
     double best = 1e30;
     int best_b = backend_;
@@ -1116,6 +1121,9 @@ int Plan::run_transpose(int ttype, void* in, void* out, void* aux) {
     auto it = handles_.find(ttype);
     if (it == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
     ReshapeHandle& h = *it->second;
+    static const char* const names[7] = {"Transpose Z_TO_X", "Transpose Z_TO_Y", "Transpose Y_TO_X", "", "Transpose X_TO_Y",
+                                         "Transpose Y_TO_Z", "Transpose X_TO_Z"};  // reshape_plan_base.F90:229
+    TraceRange trace(names[ttype + 3], kColorTransposeType[ttype + 3]);
     stat_launches_ += h.kernel_launches();
     stat_local_ += h.local_elements() * base_storage_;
     stat_remote_ += h.remote_elements() * base_storage_;
@@ -1127,6 +1135,9 @@ int Plan::run_reshape(int rtype, void* in, void* out, void* aux) {
     if (it == rhandles_.end()) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
     ReshapeHandle& h = *it->second;
     const int64_t es = (rtype == R_X_BRICKS_TO_PENCILS || rtype == R_X_PENCILS_TO_BRICKS) ? base_storage_init_ : base_storage_;
+    static const char* const names[4] = {"Reshape X_BRICKS_TO_PENCILS", "Reshape X_PENCILS_TO_BRICKS",
+                                         "Reshape Z_PENCILS_TO_BRICKS", "Reshape Z_BRICKS_TO_PENCILS"};
+    TraceRange trace(names[rtype - R_X_BRICKS_TO_PENCILS], kColorReshapeType[rtype - R_X_BRICKS_TO_PENCILS]);
     stat_launches_ += h.kernel_launches();
     stat_local_ += h.local_elements() * es;
     stat_remote_ += h.remote_elements() * es;
@@ -1136,6 +1147,7 @@ int Plan::run_reshape(int rtype, void* in, void* out, void* aux) {
 int Plan::run_fft(int dim, void* a, void* b, int sign) {
     FftExecutor* f = fft_[fft_mapping_[dim]].get();
     if (!f) return DTFFT_SUCCESS;
+    TraceRange trace("FFT", kColorFft);  // abstract_executor.F90:230
     return f->execute(a, b, sign);
 }
 
@@ -1208,6 +1220,7 @@ int Plan::run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void
 
 int Plan::transpose(void* in, void* out, int ttype, void* aux) {
     // transpose_private, dtfft_plan.F90:695-747
+    TraceRange trace_api("dtfft_transpose", kColorTranspose);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     const int at = std::abs(ttype);
@@ -1227,6 +1240,7 @@ int Plan::transpose(void* in, void* out, int ttype, void* aux) {
 
 int Plan::reshape(void* in, void* out, int rtype, void* aux) {
     // reshape_private, dtfft_plan.F90:489-544
+    TraceRange trace_api("dtfft_reshape", kColorTranspose);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (!is_reshape_enabled_) return DTFFT_ERROR_RESHAPE_NOT_SUPPORTED;
@@ -1246,6 +1260,7 @@ int Plan::reshape(void* in, void* out, int rtype, void* aux) {
 
 int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     // execute_ptr, dtfft_plan.F90:771-837
+    TraceRange trace_api("dtfft_execute", kColorExecute);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (execute_type != DTFFT_EXECUTE_FORWARD && execute_type != DTFFT_EXECUTE_BACKWARD) return DTFFT_ERROR_INVALID_EXECUTE_TYPE;
