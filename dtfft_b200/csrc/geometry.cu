@@ -310,7 +310,8 @@ struct AxisView {
     bool empty = false;
 };
 
-AxisView view_of(const RankLayout& src, const RankLayout& dst) {
+// `clip` (optional): per GLOBAL axis [lo, hi) the intersection is further restricted to.
+AxisView view_of(const RankLayout& src, const RankLayout& dst, const long long (*clip)[2] = nullptr) {
     AxisView v{};
     const int nd = src.ndims;
     long long st = 1;
@@ -327,9 +328,10 @@ AxisView view_of(const RankLayout& src, const RankLayout& dst) {
         const int A = src.axis[js];
         int jd = 0;
         while (dst.axis[jd] != A) ++jd;
-        const long long lo = std::max<long long>(src.starts[js], dst.starts[jd]);
-        const long long hi = std::min<long long>((long long)src.starts[js] + src.counts[js],
-                                                 (long long)dst.starts[jd] + dst.counts[jd]);
+        long long lo = std::max<long long>(src.starts[js], dst.starts[jd]);
+        long long hi = std::min<long long>((long long)src.starts[js] + src.counts[js],
+                                           (long long)dst.starts[jd] + dst.counts[jd]);
+        if (clip) lo = std::max(lo, clip[A][0]), hi = std::min(hi, clip[A][1]);
         v.lo[A] = lo, v.n[A] = hi - lo;
         if (hi <= lo) v.empty = true;
     }
@@ -337,9 +339,18 @@ AxisView view_of(const RankLayout& src, const RankLayout& dst) {
 }
 }  // namespace
 
+namespace {
+Box intersect_box_clipped(const RankLayout& src, const RankLayout& dst, const long long (*clip)[2], bool* transposing);
+}
+
 Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposing) {
+    return intersect_box_clipped(src, dst, nullptr, transposing);
+}
+
+namespace {
+Box intersect_box_clipped(const RankLayout& src, const RankLayout& dst, const long long (*clip)[2], bool* transposing) {
     const int nd = src.ndims;
-    const AxisView v = view_of(src, dst);
+    const AxisView v = view_of(src, dst, clip);
     const int a = src.axis[0], b = dst.axis[0];
     if (transposing) *transposing = a != b;
     Box x;
@@ -366,6 +377,44 @@ Box intersect_box(const RankLayout& src, const RankLayout& dst, bool* transposin
         x.os0 = 1, x.os1 = v.dstride[A1], x.os2 = A2 >= 0 ? v.dstride[A2] : 0;
     }
     return x;
+}
+}  // namespace
+
+Box local_producer_box(const Pencil& send, const Pencil& recv, int k, int nchunks) {
+    const int nd = recv.ndims;
+    const RankLayout src = layout_of(send), dst = layout_of(recv);
+    const long long n = recv.counts[nd - 1];
+    const long long lo = n * k / nchunks, hi = n * (k + 1) / nchunks;
+    if (hi <= lo) return Box{};
+    long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
+    const int A = dst.axis[nd - 1];  // global axis of the destination's slowest local axis
+    clip[A][0] = recv.starts[nd - 1] + lo, clip[A][1] = recv.starts[nd - 1] + hi;
+    bool tr = false;
+    return intersect_box_clipped(src, dst, clip, &tr);
+}
+
+std::vector<Box> local_consumer_boxes(const Pencil& send, const Pencil& recv, const std::vector<Pencil>& senders_src,
+                                      int k, int nchunks) {
+    const RankLayout src = layout_of(send), dst = layout_of(recv);
+    std::vector<Box> out;
+    for (const Pencil& sp : senders_src) {
+        // what sender `sp` delivers with its chunk k: its source pencil with the slowest axis cut
+        const int nd = sp.ndims;
+        const RankLayout sl = layout_of(sp);
+        const long long n = sp.counts[nd - 1];
+        const long long lo = n * k / nchunks, hi = n * (k + 1) / nchunks;
+        if (hi <= lo) {
+            out.push_back(Box{});
+            continue;
+        }
+        long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
+        for (int j = 0; j < nd; ++j) clip[sl.axis[j]][0] = sp.starts[j], clip[sl.axis[j]][1] = (long long)sp.starts[j] + sp.counts[j];
+        const int A = sl.axis[nd - 1];
+        clip[A][0] = sp.starts[nd - 1] + lo, clip[A][1] = sp.starts[nd - 1] + hi;
+        bool tr = false;
+        out.push_back(intersect_box_clipped(src, dst, clip, &tr));
+    }
+    return out;
 }
 
 RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like) {

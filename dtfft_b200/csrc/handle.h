@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <vector>
@@ -75,8 +76,39 @@ public:
     int fused_chunk(void* in, void* out, int k, int nchunks, int max_ctas, cudaStream_t stream);
     int fused_end(cudaStream_t stream);
 
+    // ---- pipelining a LOCAL transposition with the exchange next to it (geometry.h) ---------
+    // A handle without exchange whose kernel is a tiled transpose can run in pieces: the piece that
+    // writes chunk k of its destination's slowest axis (producer of a chunked exchange), or the
+    // piece that reads what chunk k of a preceding chunked exchange delivered (consumer).
+    bool is_local_transpose() const { return created_ && !has_exchange_ && is_transpose_ && send_elems_ > 0; }
+    long long dest_slow_extent() const {
+        const Pencil& r = recv_by_member_[(size_t)me_];
+        return r.ndims > 0 ? r.counts[r.ndims - 1] : 1;
+    }
+    int local_produce(const void* in, void* out, int k, int nchunks, cudaStream_t stream);
+    int local_consume(const void* in, void* out, int k, int nchunks, const std::vector<Pencil>& senders_src,
+                      cudaStream_t stream);
+    const std::vector<Pencil>& send_by_member() const { return send_by_member_; }
+    // Smallest slowest-axis extent of the members' source pencils, 0 if any member's source or
+    // destination pencil is empty: what every member can compute alike to agree on a chunk count.
+    long long min_member_slow_extent() const {
+        long long m = -1;
+        for (size_t i = 0; i < send_by_member_.size(); ++i) {
+            const Pencil& sp = send_by_member_[i];
+            if (sp.size() == 0 || recv_by_member_[i].size() == 0) return 0;
+            const long long n = sp.counts[sp.ndims - 1];
+            m = m < 0 ? n : std::min(m, n);
+        }
+        return m < 0 ? 0 : m;
+    }
+    // "All members' chunk has landed" between the chunks of a chunked exchange (consumer pipelining).
+    int fused_chunk_landed(cudaStream_t stream) { return fused_end(stream); }
+
 private:
     int execute_fused(void* in, void* out, cudaStream_t stream);
+    // piece kernels of a local transposition: [0] producer side, [1] consumer side, keyed by nchunks
+    std::map<int, std::vector<std::unique_ptr<Kernel>>> local_pieces_[2];
+    std::vector<Pencil> send_by_member_;
 
     HandleContext ctx_;
     bool created_ = false, has_exchange_ = false, is_transpose_ = true;

@@ -121,6 +121,9 @@ public:
     // Boxes of chunk k of n of the stage-overlapped fused transposition `ttype` (geometry.h: chunk_boxes).
     int describe_chunk(int ttype, int k, int nchunks, std::vector<int>* members, std::vector<Box>* boxes,
                        long long* chunk_offset) const;
+    // Pieces of a LOCAL transposition pipelined with the exchange `t_exchange` next to it (geometry.h:
+    // local_producer_box / local_consumer_boxes): side 0 = producer, 1 = consumer.
+    int describe_local_piece(int t_local, int t_exchange, int side, int k, int nchunks, std::vector<Box>* boxes) const;
     std::vector<int> transpose_types() const;
 
 private:
@@ -158,6 +161,8 @@ private:
     int run_fft(int dim, void* a, void* b, int sign);
     // FFT a -> b followed by the transposition b -> c.  With the NVLINK_FUSED backend the two
     // are pipelined chunk by chunk over two streams (stage overlap); otherwise run back to back.
+    int run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* aux);
+    int ensure_overlap_resources(long long nch, bool consumer);
     int run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void* c, void* aux);
     int execute_schedule(void* in, void* out, bool fwd, void* a1, void* a2, bool inplace);
     bool graphs_usable() const;
@@ -236,6 +241,12 @@ private:
     int64_t stat_graph_replays_ = 0;
     // stage overlap
     int overlap_chunks_ = 1, overlap_ctas_ = 0;
+    // DTFFTB_TRANSPOSE_OVERLAP=n (opt-in): pipeline a local transposition with the exchanging one next to
+    // it in transpose-only schedules (Plan::run_transpose_pair)
+    int transpose_overlap_ = 1;
+    cudaStream_t bar_stream_ = nullptr;
+    std::vector<cudaEvent_t> landed_events_;
+    cudaEvent_t pair_start_ = nullptr;
     bool overlap_user_set_ = false;
     cudaStream_t xfer_stream_ = nullptr;
     std::vector<cudaEvent_t> chunk_events_;

@@ -212,6 +212,39 @@ def main():
             checked += 1
         os.environ.pop("DTFFTB_RESHAPE_SHORTCUTS", None)
 
+    # DTFFTB_TRANSPOSE_OVERLAP: a local transposition pipelined with the exchange next to it on a slab-shaped
+    # grid 1 x 1 x P (forward: X->Y local producer of Y->Z; backward: Z->Y exchange feeding Y->X), 3 uneven chunks
+    if Backend.NVLINK_FUSED in backends:
+        os.environ["DTFFTB_TRANSPOSE_OVERLAP"] = "3"
+        dims = [40, 36, 32 * world + 1]
+        plan = PlanC2C(dims, comm=comm, config=Config(backend=Backend.NVLINK_FUSED, enable_z_slab=False))
+        os.environ.pop("DTFFTB_TRANSPOSE_OVERLAP")
+        assert plan.grid_dims == [1, 1, world], plan.grid_dims
+        G = P.global_array(dims, np.complex128, kind="random")
+        pencils = [oracle_pencil(plan.get_pencil(lay[d])) for d in range(3)]
+        x, want = P.pencil_slice(G, pencils[0]), P.pencil_slice(G, pencils[2])
+        ab, at = dev_buf(plan, plan.alloc_bytes, x)
+        bb, bt = dev_buf(plan, plan.alloc_bytes)
+        cb, ct = dev_buf(plan, plan.alloc_bytes)
+        for _ in range(2):  # twice: the second call reuses the piece kernels and the barrier epochs
+            bt.fill_(0xAB)
+            ct.fill_(0xAB)
+            torch.cuda.synchronize()
+            dist.barrier()
+            plan.execute(at, bt, Execute.FORWARD)
+            sync(plan)
+            assert plan.overlapped_stages == 1, plan.overlapped_stages
+            assert np.array_equal(host(bt, np.complex128, want.size).view(np.uint8), want.view(np.uint8)), ("pair fwd", rank)
+            plan.execute(bt, ct, Execute.BACKWARD)
+            sync(plan)
+            assert plan.overlapped_stages == 1
+            assert np.array_equal(host(ct, np.complex128, x.size).view(np.uint8), x.view(np.uint8)), ("pair bwd", rank)
+        assert plan.peer_error() == 0
+        for b_ in (ab, bb, cb):
+            plan.mem_free(b_)
+        plan.destroy()
+        checked += 1
+
     # DTFFT_PATIENT: timed backend choice (run_autotune_backend), then a correct transposition
     plan = PlanC2C([128, 64, 96], comm=comm, effort=Effort.PATIENT, config=Config(enable_z_slab=False))
     picked = plan.backend

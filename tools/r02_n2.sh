@@ -11,3 +11,5 @@ timeout 300 $TR --master-port 29540 bench.py --gpus 2 > gpurun_out/r02a_bench_n2
 # 5. barriers folded into the fused kernel (opt-in, first run ever: keep it under its own timeout): parity, then A/B
 DTFFTB_FUSED_SYNC=1 DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 300 $TR --master-port 29541 tests/_gpu_worker.py 2>&1 | tail -5
 DTFFTB_FUSED_SYNC=1 timeout 300 $TR --master-port 29542 bench.py --gpus 2 > gpurun_out/r02a_bench_n2_fusedsync.json 2> gpurun_out/r02a_bench_n2_fusedsync.err; cut -c 1-600 gpurun_out/r02a_bench_n2_fusedsync.json; tail -3 gpurun_out/r02a_bench_n2_fusedsync.err
+# 6. local transposition pipelined with the exchange next to it (opt-in, first run ever): A/B of the cycle
+for n in 2 4 8; do DTFFTB_TRANSPOSE_OVERLAP=$n timeout 300 $TR --master-port 2955$n bench.py --gpus 2 --backend nvlink > gpurun_out/r02a_bench_n2_pair$n.json 2> gpurun_out/r02a_bench_n2_pair$n.err; cut -c 1-330 gpurun_out/r02a_bench_n2_pair$n.json; tail -2 gpurun_out/r02a_bench_n2_pair$n.err; done
