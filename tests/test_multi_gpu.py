@@ -27,6 +27,6 @@ def test_all_backends_multi_gpu(cuda):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "_gpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-6000:]
     assert out.stdout.count("multi-GPU plan checks OK") == world
