@@ -1,7 +1,9 @@
 # Round 2, first 2-GPU call:  gpurun --gpus 2 --timeout 900 -- 'bash tools/r02_n2.sh'
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 # 1. every backend through the plan API, brick reshapes with and without the pack-free / unpack-free shortcuts
-timeout 500 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -30
+timeout 700 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -30
+# 1b. the same worker with the checks of the features written after the round-1 GPU budget was spent
+DTFFTB_TEST_EXPERIMENTAL=1 DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 400 $TR --master-port 29520 tests/_gpu_worker.py 2>&1 | tail -8
 # 2. config 5 (bricks, NCCL backends): shortcuts on / off
 for s in 1 0; do DTFFTB_RESHAPE_SHORTCUTS=$s timeout 300 $TR --master-port 2952$s tools/configs_bench.py --configs c5 --backends nccl,nccl_pipe --overlap 1 > gpurun_out/r02a_c5_shortcuts${s}_n2.jsonl 2> gpurun_out/r02a_c5_shortcuts${s}_n2.err; cut -c 1-330 gpurun_out/r02a_c5_shortcuts${s}_n2.jsonl; tail -3 gpurun_out/r02a_c5_shortcuts${s}_n2.err; done
 # 3. CUDA-graph replay of the NCCL backends on the launch-bound half-size configs
