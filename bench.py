@@ -396,6 +396,8 @@ def run_ours(args):
                                "(BASELINE configs[1]) through dtfft_execute FORWARD + BACKWARD",
                    "global_dims": dims, "grid": grid, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
                    "backend": R["backend"], "transposition_ms": per_type,
+                   "switches": {k: os.environ[k] for k in ("DTFFTB_TRANSPOSE_OVERLAP", "DTFFTB_FUSED_SYNC", "DTFFTB_CACHE_HINT",
+                                                            "DTFFTB_GRAPHS", "DTFFTB_TILE") if k in os.environ},
                    "backends_ms_per_step": {k: v["ms"] for k, v in results.items()},
                    "l2": f"working set 2 x {n_local * ES / 2**20:.0f} MiB per transposition per GPU >> 126 MB L2 (no flush needed)"
                    if n_local * ES > 2**28 else
