@@ -1,4 +1,5 @@
 # Round 2, first 1-GPU call (~8 min of box time):  gpurun --timeout 900 -- 'bash tools/r02_n1.sh'
+mkdir -p gpurun_out
 # 1. the whole GPU suite (includes everything written CPU-only at the end of round 1)
 timeout 500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 # 2. the bench line + its launch list

@@ -1,4 +1,5 @@
 # Round 2, first 2-GPU call:  gpurun --gpus 2 --timeout 900 -- 'bash tools/r02_n2.sh'
+mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 # 1. every backend through the plan API, brick reshapes with and without the pack-free / unpack-free shortcuts
 timeout 700 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -30

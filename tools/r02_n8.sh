@@ -1,4 +1,5 @@
 # Round 2, 8-GPU call:  gpurun --gpus 8 --timeout 900 -- 'bash tools/r02_n8.sh'
+mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 # 1. first run of the process-grid search on real GPUs: 512^3 at 8 ranks, 1x8 vs 8x1 vs 2x4 vs 4x2
 DTFFTB_LOG=1 timeout 300 $TR --master-port 29551 tools/grid_search_probe.py > gpurun_out/r02a_grid_search_n8.txt 2>&1; tail -25 gpurun_out/r02a_grid_search_n8.txt
