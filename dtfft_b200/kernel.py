@@ -48,6 +48,11 @@ def _ptr(buf) -> int:
         if not buf.is_cuda:
             raise TypeError("dtfft_b200 kernels take device buffers only (no CPU fallback)")
         return int(buf.data_ptr())
+    iface = getattr(buf, "__cuda_array_interface__", None)  # cupy / numba arrays, like the reference's cupy inputs
+    if iface is not None:
+        return int(iface["data"][0])
+    if hasattr(buf, "__array_interface__"):
+        raise TypeError("dtfft_b200 takes device buffers only (no CPU fallback): got a host array")
     raise TypeError(f"unsupported buffer type {type(buf)}")
 
 
