@@ -56,3 +56,38 @@ def test_library_then_torch_share_one_nccl():
             "assert len(set(n)) == 1, set(n); print('one nccl')")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
     assert out.returncode == 0 and "one nccl" in out.stdout, out.stderr[-2000:]
+
+
+def test_plugin_abi_argument_validation():
+    """Error behaviour of the backend / executor plugin entry points that needs no device: NULL handles,
+    backend types outside the NCCL family, element sizes, the R2R refusal of the cuFFT executor
+    (src/interfaces/fft/cufft/dtfft_executor_cufft_m.F90:94-98), bad precision / rank."""
+    import ctypes as C
+
+    import dtfft_b200
+
+    L = dtfft_b200.lib()
+    vp, i32p, i64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.dtfftb_backend_create.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, i32p, i64p, i64p, i64p, i64p, C.c_int64]
+    L.dtfftb_backend_create.restype = C.c_int
+    L.dtfftb_executor_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, i32p,
+                                         i32p, i32p, vp]
+    L.dtfftb_executor_create.restype = C.c_int
+    h = vp(0)
+    one = (C.c_int64 * 1)(0)
+    fake_comm = vp(0x1000)  # never dereferenced before the checks below fail
+    usage = L.dtfftb_backend_create(None, 24, fake_comm, 0, 1, None, one, one, one, one, 8)
+    assert usage != 0
+    assert L.dtfftb_backend_create(C.byref(h), 23, fake_comm, 0, 1, None, one, one, one, one, 8) == 202   # MPI_A2A: not here
+    assert L.dtfftb_backend_create(C.byref(h), 24, None, 0, 1, None, one, one, one, one, 8) == usage      # no communicator
+    assert L.dtfftb_backend_create(C.byref(h), 24, fake_comm, 1, 1, None, one, one, one, one, 8) == usage  # rank >= size
+    assert L.dtfftb_backend_create(C.byref(h), 24, fake_comm, 0, 1, None, one, one, one, one, 12) == usage  # element size
+    assert h.value in (None, 0)
+    n = (C.c_int32 * 2)(8, 8)
+    e = vp(0)
+    assert L.dtfftb_executor_create(None, 1, 0, 1, 8, 8, 4, n, n, n, None) == usage
+    assert L.dtfftb_executor_create(C.byref(e), 3, 0, 1, 8, 8, 4, n, n, n, None) == usage       # fft_rank
+    assert L.dtfftb_executor_create(C.byref(e), 1, 2, 1, 8, 8, 4, n, n, n, None) == 101         # R2R: DTFFT_ERROR_R2R_FFT_NOT_SUPPORTED
+    assert L.dtfftb_executor_create(C.byref(e), 1, 0, 7, 8, 8, 4, n, n, n, None) == 6           # precision
+    assert L.dtfftb_executor_create(C.byref(e), 1, 0, 1, 8, 8, 4, None, n, n, None) == usage
+    assert e.value in (None, 0)
