@@ -7,6 +7,9 @@
  *     dtfftb_comm_from_mpi(MPI_COMM_WORLD, &c);
  *     dtfft_create_plan_c2c(3, dims, &c.comm, DTFFT_DOUBLE, DTFFT_ESTIMATE, DTFFT_EXECUTOR_NONE, &plan);
  *
+ * The plan keeps `c.comm.ctx` (= &c) for its later collectives (dtfft_mem_alloc with the NVLINK_FUSED
+ * backend, dtfft_destroy): `c` must outlive every plan created from it, like the MPI_Comm itself.
+ *
  * A cartesian communicator (MPI_Cart_create) is forwarded as cart_ndims / cart_dims in dtFFT's
  * order (dims[0] fastest = LAST dimension of the MPI grid is NOT reversed: the reference reads
  * MPI_Cart_get verbatim, src/dtfft_transpose_plan.F90:139-158).
