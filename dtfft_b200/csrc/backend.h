@@ -41,6 +41,7 @@ public:
                const std::vector<int64_t>& send_displs, const std::vector<int64_t>& send_counts,
                const std::vector<int64_t>& recv_displs, const std::vector<int64_t>& recv_counts, int64_t base_storage);
     void set_unpack_kernel(Kernel* k) { unpack_ = k; }
+    bool has_unpack_kernel() const { return unpack_ != nullptr; }
     // abstract_backend%execute: `in` packed send buffer, `out` final destination (pipelined)
     // or receive buffer (plain), `aux` receive workspace of the pipelined flavour.
     int execute(void* in, void* out, cudaStream_t stream, void* aux);

@@ -93,6 +93,9 @@ int dtfftb_backend_get_aux_bytes(dtfftb_backend_t backend, int64_t* aux_bytes) {
 int dtfftb_backend_execute(dtfftb_backend_t backend, void* in, void* out, void* stream, void* aux) {
     if (!backend || !in || !out) return DTFFT_ERROR_INVALID_USAGE;
     if (backend->b.is_pipelined() && !aux) return DTFFT_ERROR_INVALID_AUX;
+    // the pipelined flavour unpacks block by block: a caller with nothing to unpack (unpack-free
+    // reshape) hands it a KERNEL_DUMMY kernel like the reference does (reshape_handle_generic.F90:623)
+    if (backend->b.is_pipelined() && !backend->b.has_unpack_kernel()) return DTFFT_ERROR_INVALID_USAGE;
     return backend->b.execute(in, out, static_cast<cudaStream_t>(stream), aux);
 }
 
