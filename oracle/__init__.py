@@ -15,5 +15,10 @@ cross-checking two independent restatements: the kernel-level index maps of
 ``src/include/_dtfft_kernel_host_routines.inc`` driven by the block geometry of
 ``src/dtfft_reshape_handle_generic.F90`` must reproduce, bit for bit, the global-array
 redistribution that the host MPI-datatype path
-(``src/dtfft_reshape_handle_datatype.F90``) performs by construction.
+(``src/dtfft_reshape_handle_datatype.F90``) performs by construction -- and that
+construction is restated too (``datatype_path.py``: the derived datatypes, displacements and
+all-to-all(w) of that file) and checked against the redistribution
+(tests/test_oracle_datatype_path.py).  On the GPU box the oracle is additionally pinned by
+golden vectors and digests produced by the reference's own regenerated device kernels
+(tests/golden/, tests/test_oracle_golden.py, tests/test_vs_reference_kernels_gpu.py).
 """
