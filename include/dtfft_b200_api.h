@@ -215,73 +215,119 @@ typedef struct {
     dtfft_access_mode_t access_mode;
 } dtfft_config_t;
 
+/* replaces dtfft_get_version, include/dtfft.h:52 */
 int32_t dtfft_get_version(void);
 
 /* constructors: include/dtfft.h:397-515 */
+/* replaces dtfft_create_plan_r2r, include/dtfft.h:398 */
 dtfft_error_t dtfft_create_plan_r2r(int8_t ndims, const int32_t* dims, const dtfft_r2r_kind_t* kinds, dtfft_comm_t comm,
                                     dtfft_precision_t precision, dtfft_effort_t effort, dtfft_executor_t executor,
                                     dtfft_plan_t* plan);
+/* replaces dtfft_create_plan_r2r_pencil, include/dtfft.h:423 */
 dtfft_error_t dtfft_create_plan_r2r_pencil(const dtfft_pencil_t* pencil, const dtfft_r2r_kind_t* kinds,
                                            dtfft_comm_t comm, dtfft_precision_t precision, dtfft_effort_t effort,
                                            dtfft_executor_t executor, dtfft_plan_t* plan);
+/* replaces dtfft_create_plan_c2c, include/dtfft.h:445 */
 dtfft_error_t dtfft_create_plan_c2c(int8_t ndims, const int32_t* dims, dtfft_comm_t comm, dtfft_precision_t precision,
                                     dtfft_effort_t effort, dtfft_executor_t executor, dtfft_plan_t* plan);
+/* replaces dtfft_create_plan_c2c_pencil, include/dtfft.h:466 */
 dtfft_error_t dtfft_create_plan_c2c_pencil(const dtfft_pencil_t* pencil, dtfft_comm_t comm,
                                            dtfft_precision_t precision, dtfft_effort_t effort,
                                            dtfft_executor_t executor, dtfft_plan_t* plan);
+/* replaces dtfft_create_plan_r2c, include/dtfft.h:487 */
 dtfft_error_t dtfft_create_plan_r2c(int8_t ndims, const int32_t* dims, dtfft_comm_t comm, dtfft_precision_t precision,
                                     dtfft_effort_t effort, dtfft_executor_t executor, dtfft_plan_t* plan);
+/* replaces dtfft_create_plan_r2c_pencil, include/dtfft.h:509 */
 dtfft_error_t dtfft_create_plan_r2c_pencil(const dtfft_pencil_t* pencil, dtfft_comm_t comm,
                                            dtfft_precision_t precision, dtfft_effort_t effort,
                                            dtfft_executor_t executor, dtfft_plan_t* plan);
 
 /* execution: include/dtfft.h:555-645 */
+/* replaces dtfft_execute, include/dtfft.h:555 */
 dtfft_error_t dtfft_execute(dtfft_plan_t plan, void* in, void* out, dtfft_execute_t execute_type, void* aux);
+/* replaces dtfft_transpose, include/dtfft.h:570 */
 dtfft_error_t dtfft_transpose(dtfft_plan_t plan, void* in, void* out, dtfft_transpose_t transpose_type, void* aux);
+/* replaces dtfft_transpose_start, include/dtfft.h:591 */
 dtfft_error_t dtfft_transpose_start(dtfft_plan_t plan, void* in, void* out, dtfft_transpose_t transpose_type,
                                     void* aux, dtfft_request_t* request);
+/* replaces dtfft_transpose_end, include/dtfft.h:602 */
 dtfft_error_t dtfft_transpose_end(dtfft_plan_t plan, dtfft_request_t request);
+/* replaces dtfft_reshape, include/dtfft.h:617 */
 dtfft_error_t dtfft_reshape(dtfft_plan_t plan, void* in, void* out, dtfft_reshape_t reshape_type, void* aux);
+/* replaces dtfft_reshape_start, include/dtfft.h:635 */
 dtfft_error_t dtfft_reshape_start(dtfft_plan_t plan, void* in, void* out, dtfft_reshape_t reshape_type, void* aux,
                                   dtfft_request_t* request);
+/* replaces dtfft_reshape_end, include/dtfft.h:645 */
 dtfft_error_t dtfft_reshape_end(dtfft_plan_t plan, dtfft_request_t request);
+/* replaces dtfft_destroy, include/dtfft.h:654 */
 dtfft_error_t dtfft_destroy(dtfft_plan_t* plan);
 
 /* sizes and metadata: include/dtfft.h:668-918 */
+/* replaces dtfft_get_local_sizes, include/dtfft.h:668 */
 dtfft_error_t dtfft_get_local_sizes(dtfft_plan_t plan, int32_t* in_starts, int32_t* in_counts, int32_t* out_starts,
                                     int32_t* out_counts, size_t* alloc_size);
+/* replaces dtfft_get_alloc_size, include/dtfft.h:678 */
 dtfft_error_t dtfft_get_alloc_size(dtfft_plan_t plan, size_t* alloc_size);
+/* replaces dtfft_get_aux_size, include/dtfft.h:688 */
 dtfft_error_t dtfft_get_aux_size(dtfft_plan_t plan, size_t* aux_size);
+/* replaces dtfft_get_aux_bytes, include/dtfft.h:698 */
 dtfft_error_t dtfft_get_aux_bytes(dtfft_plan_t plan, size_t* aux_bytes);
+/* replaces dtfft_get_aux_size_reshape, include/dtfft.h:708 */
 dtfft_error_t dtfft_get_aux_size_reshape(dtfft_plan_t plan, size_t* aux_size);
+/* replaces dtfft_get_aux_bytes_reshape, include/dtfft.h:718 */
 dtfft_error_t dtfft_get_aux_bytes_reshape(dtfft_plan_t plan, size_t* aux_bytes);
+/* replaces dtfft_get_aux_size_transpose, include/dtfft.h:728 */
 dtfft_error_t dtfft_get_aux_size_transpose(dtfft_plan_t plan, size_t* aux_size);
+/* replaces dtfft_get_aux_bytes_transpose, include/dtfft.h:738 */
 dtfft_error_t dtfft_get_aux_bytes_transpose(dtfft_plan_t plan, size_t* aux_bytes);
+/* replaces dtfft_get_pencil, include/dtfft.h:806 */
 dtfft_error_t dtfft_get_pencil(dtfft_plan_t plan, dtfft_layout_t layout, dtfft_pencil_t* pencil);
+/* replaces dtfft_get_element_size, include/dtfft.h:817 */
 dtfft_error_t dtfft_get_element_size(dtfft_plan_t plan, size_t* element_size);
+/* replaces dtfft_get_alloc_bytes, include/dtfft.h:831 */
 dtfft_error_t dtfft_get_alloc_bytes(dtfft_plan_t plan, size_t* alloc_bytes);
+/* replaces dtfft_mem_alloc, include/dtfft.h:843 */
 dtfft_error_t dtfft_mem_alloc(dtfft_plan_t plan, size_t alloc_bytes, void** ptr);
+/* replaces dtfft_mem_free, include/dtfft.h:854 */
 dtfft_error_t dtfft_mem_free(dtfft_plan_t plan, void* ptr);
+/* replaces dtfft_report, include/dtfft.h:864 */
 dtfft_error_t dtfft_report(dtfft_plan_t plan);
+/* replaces dtfft_get_z_slab_enabled, include/dtfft.h:526 */
 dtfft_error_t dtfft_get_z_slab_enabled(dtfft_plan_t plan, bool* is_z_slab_enabled);
+/* replaces dtfft_get_y_slab_enabled, include/dtfft.h:537 */
 dtfft_error_t dtfft_get_y_slab_enabled(dtfft_plan_t plan, bool* is_y_slab_enabled);
+/* replaces dtfft_get_executor, include/dtfft.h:875 */
 dtfft_error_t dtfft_get_executor(dtfft_plan_t plan, dtfft_executor_t* executor);
+/* replaces dtfft_get_precision, include/dtfft.h:886 */
 dtfft_error_t dtfft_get_precision(dtfft_plan_t plan, dtfft_precision_t* precision);
+/* replaces dtfft_get_dims, include/dtfft.h:901 */
 dtfft_error_t dtfft_get_dims(dtfft_plan_t plan, int8_t* ndims, const int32_t* dims[]);
+/* replaces dtfft_get_grid_dims, include/dtfft.h:917 */
 dtfft_error_t dtfft_get_grid_dims(dtfft_plan_t plan, int8_t* ndims, const int32_t* grid_dims[]);
+/* replaces dtfft_get_stream, include/dtfft.h:1096 */
 dtfft_error_t dtfft_get_stream(dtfft_plan_t plan, dtfft_stream_t* stream);
+/* replaces dtfft_get_platform, include/dtfft.h:1107 */
 dtfft_error_t dtfft_get_platform(dtfft_plan_t plan, dtfft_platform_t* platform);
+/* replaces dtfft_get_backend, include/dtfft.h:1122 */
 dtfft_error_t dtfft_get_backend(dtfft_plan_t plan, dtfft_backend_t* backend);
+/* replaces dtfft_get_reshape_backend, include/dtfft.h:1133 */
 dtfft_error_t dtfft_get_reshape_backend(dtfft_plan_t plan, dtfft_backend_t* backend);
+/* replaces dtfft_get_backend_pipelined, include/dtfft.h:1154 */
 dtfft_error_t dtfft_get_backend_pipelined(const dtfft_backend_t backend, bool* is_pipe);
 
+/* replaces dtfft_get_error_string, include/dtfft.h:759 */
 const char* dtfft_get_error_string(dtfft_error_t error_code);
+/* replaces dtfft_get_precision_string, include/dtfft.h:768 */
 const char* dtfft_get_precision_string(dtfft_precision_t precision);
+/* replaces dtfft_get_executor_string, include/dtfft.h:777 */
 const char* dtfft_get_executor_string(dtfft_executor_t executor);
+/* replaces dtfft_get_backend_string, include/dtfft.h:1143 */
 const char* dtfft_get_backend_string(dtfft_backend_t backend);
 
 /* configuration: include/dtfft.h:1398-1407 */
+/* replaces dtfft_create_config, include/dtfft.h:1398 */
 dtfft_error_t dtfft_create_config(dtfft_config_t* config);
+/* replaces dtfft_set_config, include/dtfft.h:1407 */
 dtfft_error_t dtfft_set_config(const dtfft_config_t* config);
 
 /* ---- extensions of this library (not in the reference) --------------------------------- */
