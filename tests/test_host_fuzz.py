@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from dtfft_b200.plan import Config, Executor, Layout, Pencil, PlanC2C, PlanR2C, Precision
+from oracle import datatype_path as D
 from oracle import layout as L
 from oracle import pipeline as P
 from tests.test_plan_host import LAYOUT_OF_PENCIL, dry_world, replay_fused
@@ -71,9 +72,16 @@ def test_random_default_and_cart_decompositions(dims, nranks, z_slab, cart, pipe
         got = replay_fused(plans, t, src, [w.size for w in want], np.complex128)
         # three-step NCCL path with the (identical) reference tables
         gen = P.transpose_generic(src, list(dims), comm_dims, t, pipelined=pipelined)
+        # the reference's host MPI-datatype path itself (its derived datatypes restated)
+        allp = [L.make_pencils(list(dims), comm_dims, r) for r in range(nranks)]
+        si, ri = L.transpose_pencil_ids(t)
+        groups = [L.comm_members(r, comm_dims, L.transpose_comm_id(t)) for r in range(nranks)]
+        dt = D.exchange(src, [p[si] for p in allp], [p[ri] for p in allp], groups, 16, ttype=t,
+                        mode=D.PACK if pipelined else D.UNPACK)
         for r in range(nranks):
             assert np.array_equal(got[r], want[r]), ("fused", L.TRANSPOSE_NAMES[t], r)
             assert np.array_equal(gen[r], want[r]), ("generic", L.TRANSPOSE_NAMES[t], r)
+            assert np.array_equal(dt[r], want[r]), ("datatype", L.TRANSPOSE_NAMES[t], r)
     Config()._commit()
 
 
