@@ -1,4 +1,6 @@
-"""Python-side helpers of the reference module on the GPU (src/interfaces/python/__init__.py):
+"""Checks of what was written after the round-1 GPU budget was spent and therefore runs on a GPU for the
+first time in this file (kept last in collection order): the two wide tile variants, and the
+Python-side helpers of the reference module on the GPU (src/interfaces/python/__init__.py):
 ``Plan.get_ndarray`` (array backed by ``dtfft_mem_alloc`` memory, here a CUDA torch tensor instead of a
 cupy array) and the ``Request`` objects of ``transpose_start`` / ``transpose_end``."""
 import gc
@@ -43,3 +45,28 @@ def test_get_ndarray_and_async_requests(cuda):
     gc.collect()
     plan.destroy()
     Config()._commit()
+
+
+def test_wide_tile_variants_agree(cuda):
+    """32 x 128 and 128 x 32 tiles (candidates of the DTFFT_EXHAUSTIVE kernel autotune since the end of
+    round 1) give the oracle's bytes for 4-, 8- and 16-byte elements on shapes that do not divide the tile."""
+    from dtfft_b200.kernel import Kernel
+    from oracle import kernels as K
+    from tests.gpu_utils import device_filled, to_device, to_host
+
+    torch = cuda
+    for dims in ([70, 45, 19], [130, 33, 5], [200, 150]):
+        n = int(np.prod(dims))
+        for dtype in (np.float32, np.float64, np.complex128):
+            src = np.random.default_rng(2).random(n).astype(dtype)
+            for kt in (K.KERNEL_PERMUTE_FORWARD, K.KERNEL_PERMUTE_BACKWARD):
+                gold = np.zeros(n, dtype)
+                K.execute(kt, dims, src, gold)
+                d_in = to_device(torch, src)
+                k = Kernel().create(dims, 0, np.dtype(dtype).itemsize, kt)
+                for cfg in [(1, 4, 16), (4, 1, 16)]:
+                    k.set_tile(*cfg)
+                    d_out = device_filled(torch, n, dtype)
+                    k.execute(d_in, d_out, sync=True)
+                    assert np.array_equal(to_host(d_out, dtype).view(np.uint8), gold.view(np.uint8)), (dims, dtype, kt, cfg)
+                k.destroy()
