@@ -586,3 +586,30 @@ def test_report_follows_the_reference_format(capfd):
     assert body["Z-slab enabled"] == "False" and body["Y-slab enabled"] == "False"
     assert body["Backend"] == "NCCL" and body["Reshape Backend"] == "NCCL"
     Config()._commit()
+
+
+@pytest.mark.parametrize("dims,nranks", [((128, 96, 40), 2), ((256, 128, 10), 4), ((64, 64, 64), 2), ((80, 70, 33), 2)])
+def test_y_slab_decomposition(dims, nranks):
+    """Y-slab optimisation (enable_y_slab, src/dtfft_transpose_plan.F90:182-191): when both x and y are long
+    enough the grid is 1 x P x 1, the plan ends in Y pencils (execute = X -> Y only, dtfft_plan.F90:856-862,
+    get_local_sizes :1868-1876 with is_y_slab) and in-place transpose-only execution is refused (:800-804)."""
+    cfg = Config(enable_z_slab=False, enable_y_slab=True)
+    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True))
+    comm_dims, is_z, is_y = L.choose_grid(list(dims), nranks, cuda=True, z_slab=False, y_slab=True)
+    G = P.global_array(dims, np.complex128, kind="index")
+    for r, plan in enumerate(plans):
+        assert plan.grid_dims == comm_dims and plan.y_slab_enabled == is_y and not plan.z_slab_enabled
+        gold = L.make_pencils(list(dims), comm_dims, r)
+        ins, inc, outs, outc, alloc = plan.local_sizes
+        last = gold[1] if is_y else gold[2]
+        assert (ins, inc) == (gold[0].starts, gold[0].counts) and (outs, outc) == (last.starts, last.counts)
+        assert alloc == max(p.size for p in gold)
+    if is_y:
+        assert comm_dims == [1, nranks, 1]
+    for t in (1, -1, 2, -2):
+        src = P.scatter_input(G, list(dims), comm_dims, t)
+        want = P.transpose_datatype(G, list(dims), comm_dims, t)
+        got = replay_fused(plans, t, src, [w.size for w in want], np.complex128)
+        for r in range(nranks):
+            assert np.array_equal(got[r], want[r]), (t, r)
+    Config()._commit()

@@ -70,3 +70,36 @@ def test_wide_tile_variants_agree(cuda):
                     k.execute(d_in, d_out, sync=True)
                     assert np.array_equal(to_host(d_out, dtype).view(np.uint8), gold.view(np.uint8)), (dims, dtype, kt, cfg)
                 k.destroy()
+
+
+@pytest.mark.parametrize("dims", [[40, 36, 34], [64, 33, 50]])
+def test_y_slab_fft_matches_numpy(cuda, dims):
+    """Y-slab plans (enable_y_slab with the Z-slab off): 1-D transforms along x, X -> Y, then ONE 2-D transform
+    over (y, z) of the Y pencil (dtfft_plan.F90:2555-2556); the result stays in Y pencils (y, z, x)."""
+    from dtfft_b200.plan import Execute, Executor
+    from oracle import layout as L
+    from tests.gpu_utils import to_device, to_host
+
+    torch = cuda
+    plan = PlanC2C(dims, executor=Executor.CUFFT, config=Config(enable_z_slab=False, enable_y_slab=True))
+    assert plan.y_slab_enabled and not plan.z_slab_enabled
+    G = P.global_array(dims, np.complex128)
+    pencils = L.make_pencils(dims, [1, 1, 1], 0)
+    x = P.pencil_slice(G, pencils[0])
+    ins, inc, outs, outc, alloc = plan.local_sizes
+    assert outc == pencils[1].counts
+    a = to_device(torch, x)
+    b = torch.full((plan.alloc_bytes,), 0xAB, dtype=torch.uint8, device="cuda")
+    c = torch.full((plan.alloc_bytes,), 0xAB, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    plan.execute(a, b, Execute.FORWARD)
+    torch.cuda.ExternalStream(plan.stream).synchronize()
+    want = P.pencil_slice(np.asfortranarray(np.fft.fftn(G)), pencils[1])
+    got = to_host(b, np.complex128)[: want.size]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+    plan.execute(b, c, Execute.BACKWARD)
+    torch.cuda.ExternalStream(plan.stream).synchronize()
+    back = to_host(c, np.complex128)[: x.size] / np.prod(dims)
+    assert np.max(np.abs(back - x)) <= 5 * np.log2(float(np.prod(dims))) * 2 * np.finfo(np.float64).eps
+    plan.destroy()
+    Config()._commit()
