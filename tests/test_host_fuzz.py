@@ -126,6 +126,10 @@ def test_random_user_pencils(dims, ycuts, zcuts):
         for d in range(3):
             got = plan.get_pencil(LAYOUT_OF_PENCIL[d])
             assert (got.starts, got.counts) == (gold[d].starts, gold[d].counts), (r, d)
+    # partition check of the reference's Python test (tests/python/test_pencil_api_py.py:76-86): every layout
+    # tiles the global grid
+    for lay in LAYOUT_OF_PENCIL:
+        assert sum(p.get_pencil(lay).size for p in plans) == int(np.prod(dims)), lay
     for t in (1, -1, 2, -2):
         si, ri = L.transpose_pencil_ids(t)
         src = [P.pencil_slice(G, pencils[r][si]) for r in range(n)]

@@ -84,6 +84,10 @@ def check_brick_case(cuts, pipelined, want_strat=None, want_free=None):
     bricks1 = [L.Pencil(1, starts[r], counts[r]) for r in range(n)]
     xp, lastp = [p[0] for p in pencils], [p[nd - 1] for p in pencils]
     G = P.global_array(dims, np.float64, kind="index")
+    from dtfft_b200.plan import Layout
+    for lay in [Layout.X_BRICKS, Layout.X_PENCILS, Layout.Y_PENCILS, Layout.Z_BRICKS] + ([Layout.Z_PENCILS] if nd == 3 else []):
+        # every layout tiles the global grid (tests/python/test_pencil_api_py.py:76-86)
+        assert sum(p.get_pencil(lay).size for p in plans) == int(np.prod(dims)), lay
     alloc = [plans[r].alloc_size for r in range(n)]
     want_aux = [0] * n
 
