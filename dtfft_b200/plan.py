@@ -391,7 +391,7 @@ class Plan:
         req = C.c_void_p(0)
         _check(_lib.lib().dtfft_transpose_start(self._h, _ptr(inbuf), _ptr(outbuf), int(transpose_type),
                                                 _ptr(aux) or None, C.byref(req)), "dtfft_transpose_start")
-        return Request(req.value, str(Transpose(int(transpose_type))))
+        return Request(req.value, "Transpose." + Transpose(int(transpose_type)).name)
 
     def transpose_end(self, request):
         handle = request.handle if isinstance(request, Request) else int(getattr(request, "value", request) or 0)
@@ -401,7 +401,7 @@ class Plan:
         req = C.c_void_p(0)
         _check(_lib.lib().dtfft_reshape_start(self._h, _ptr(inbuf), _ptr(outbuf), int(reshape_type), _ptr(aux) or None,
                                               C.byref(req)), "dtfft_reshape_start")
-        return Request(req.value, str(Reshape(int(reshape_type))))
+        return Request(req.value, "Reshape." + Reshape(int(reshape_type)).name)
 
     def reshape_end(self, request):
         handle = request.handle if isinstance(request, Request) else int(getattr(request, "value", request) or 0)
