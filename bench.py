@@ -33,6 +33,8 @@ ES = 16  # complex128
 METRIC = "512^3 C2C fp64 fwd+bwd transpose cycle, effective GB/s"
 UNIT = "GB/s"
 CYCLE_BYTES = 4 * 2 * N_GLOBAL ** 3 * ES  # 17.18 GB: 4 transpositions, one read + one write each
+WORKLOAD = ("3D C2C fp64 512^3 transpose-only pencil cycle X->Y->Z->Y->X on {world} B200 "
+            "(BASELINE configs[1]) through dtfft_execute FORWARD + BACKWARD")
 
 
 def measured_peaks():
@@ -108,54 +110,122 @@ def oracle_lib():
     lib.oracle_kernel_execute.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
                                           ctypes.c_int]
+    lib.oracle_kernel_execute_blocked.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     return lib
 
 
-def cpu_cycle_times(n, reps):
-    """Time the oracle port (reference host kernels restated in C/OpenMP) on an n^3 c128 cycle."""
+CPU_VARIANTS = [0, 4, 8, 16, 32, 64]  # 0 = unblocked loops, else BLOCK_SIZE of the blocked permutes
+
+
+def cpu_cycle_times(n, reps, block=0, bufs=None):
+    """Time the oracle port (reference host kernels restated in C/OpenMP) on an n^3 c128 cycle.
+    block = 0: the unblocked loops (_dtfft_kernel_host_routines.inc); 4..64: the blocked permutes
+    (_dtfft_kernel_host_block_routines.inc)."""
     import numpy as np
 
     lib = oracle_lib()
     lib.oracle_set_num_threads(len(os.sched_getaffinity(0)))  # torchrun exports OMP_NUM_THREADS=1
     dims = (ctypes.c_int32 * 3)(n, n, n)
-    a = np.random.default_rng(1234).random(2 * n ** 3)  # n^3 complex128 as float64 pairs
-    b = np.empty_like(a)
+    if bufs is None:
+        a = np.random.default_rng(1234).random(2 * n ** 3)  # n^3 complex128 as float64 pairs
+        b = np.empty_like(a)
+    else:
+        a, b = bufs
     pa, pb = a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p)
     FWD, BWD = 7, 8
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
         for kt, (src, dst) in ((FWD, (pa, pb)), (FWD, (pb, pa)), (BWD, (pa, pb)), (BWD, (pb, pa))):
-            rc = lib.oracle_kernel_execute(kt, 3, dims, ES, src, dst, None, 0, 0)
+            if block:
+                rc = lib.oracle_kernel_execute_blocked(kt, 3, dims, ES, src, dst, block)
+            else:
+                rc = lib.oracle_kernel_execute(kt, 3, dims, ES, src, dst, None, 0, 0)
             assert rc == 0
         times.append(time.perf_counter() - t0)
     return times, lib.oracle_num_threads()
 
 
+def cpu_pick_variant(n_sample=256):
+    """The reference's host kernel times its unblocked loops and its blocked variants
+    (BLOCK_SIZE 4..64) and keeps the fastest; do the same on an n_sample^3 cycle."""
+    import numpy as np
+
+    a = np.random.default_rng(1234).random(2 * n_sample ** 3)
+    b = np.empty_like(a)
+    cpu_cycle_times(n_sample, 1, 0, (a, b))  # page faults
+    table = {}
+    for blk in CPU_VARIANTS:
+        t, _ = cpu_cycle_times(n_sample, 2, blk, (a, b))
+        table[blk] = min(t)
+    best = min(table, key=table.get)
+    return best, {("unblocked" if k == 0 else f"block_{k}"): v * 1e3 for k, v in table.items()}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself
     (Fortran 2018 + MPI) cannot be built in this image, so this is the oracle PORT of its host
-    kernels (src/include/_dtfft_kernel_host_routines.inc) with every host thread OpenMP gives."""
+    kernels (src/include/_dtfft_kernel_host_routines.inc and the blocked variants of
+    _dtfft_kernel_host_block_routines.inc, the fastest of them like the reference's own host-kernel
+    autotune) with every host thread OpenMP gives.  --steps / --warmup are honoured: a step is one
+    full 512^3 cycle (about 0.4 s)."""
+    import numpy as np
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = N_GLOBAL
-    steps = max(1, min(args.steps, 10))
-    cpu_cycle_times(n, 1)  # warm-up (page faults)
-    times, threads = cpu_cycle_times(n, steps)
+    block, table = cpu_pick_variant(256)
+    a = np.random.default_rng(1234).random(2 * n ** 3)
+    b = np.empty_like(a)
+    cpu_cycle_times(n, max(1, args.warmup), block, (a, b))
+    times, threads = cpu_cycle_times(n, max(1, args.steps), block, (a, b))
     t = sum(times) / len(times)
     val = CYCLE_BYTES / t / 1e9
+    variant = "unblocked" if block == 0 else f"block_{block}"
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, args.steps),
+        "warmup": max(1, args.warmup), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128 (opaque 16-byte moves)", "data": "synthetic",
-        "config": {"workload": "3D C2C fp64 512^3 transpose-only cycle X->Y->Z->Y->X, single process, host memory",
+        "config": {"workload": WORKLOAD.format(world=args.gpus),
+                   "where": "single process, host memory, every host thread",
+                   "host_kernel_variant": variant, "variant_ms_on_256^3": table,
                    "note": "reference CPU path = oracle port of dtFFT host kernels (reference needs Fortran+MPI: unbuildable here)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} full 512^3 cycle(s) after 1 warm-up"},
+                         "sample": f"{max(1, args.steps)} full 512^3 cycle(s) after {max(1, args.warmup)} warm-up cycle(s), "
+                                   f"host-kernel variant {variant} (fastest of unblocked / block 4..64 on a 256^3 sample)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+DPERM = [[0, 1, 2], [1, 2, 0], [2, 0, 1]]  # local axis j of pencil d is natural axis DPERM[d][j] (transpose_plan.F90:1046-1082)
+
+
+def expected_pencil(torch, pencil, d, dims, device):
+    """What rank-local pencil `d` (0 = X, 1 = Y, 2 = Z) must hold when element (x, y, z) of the global
+    array carries G = x + Nx (y + Ny z): the result of the reference's host MPI-datatype path
+    (src/dtfft_reshape_handle_datatype.F90:479-574 is a redistribution of G, nothing else).  Returned in
+    the pencil's memory order (local axis 0 fastest), float64."""
+    nat_s, nat_c = [0, 0, 0], [0, 0, 0]
+    for j in range(3):
+        nat_s[DPERM[d][j]], nat_c[DPERM[d][j]] = pencil.starts[j], pencil.counts[j]
+    ax = [torch.arange(nat_s[k], nat_s[k] + nat_c[k], device=device, dtype=torch.float64) for k in range(3)]
+    want = ax[0][None, None, :] + dims[0] * (ax[1][None, :, None] + dims[1] * ax[2][:, None, None])  # [z][y][x]
+    return want.permute(2 - DPERM[d][2], 2 - DPERM[d][1], 2 - DPERM[d][0]).reshape(-1)
+
+
+def encode(torch, buf, want):
+    """16-byte element = (G, -G - 1) as two float64: both halves identify the element."""
+    v = buf[: 2 * want.numel()].view(-1, 2)
+    v[:, 0] = want
+    v[:, 1] = -want - 1.0
+
+
+def holds(torch, buf, want):
+    v = buf[: 2 * want.numel()].view(-1, 2)
+    return bool(torch.equal(v[:, 0], want)) and bool(torch.equal(v[:, 1], -want - 1.0))
 
 
 def _plan_cycle(plan, Execute, a, b, aux):
@@ -217,14 +287,44 @@ def run_ours(args):
         a, b = (torch.as_tensor(x, device="cuda").view(torch.float64) for x in bufs)
         aux = torch.as_tensor(aux_buf, device="cuda")
         n_local = nbytes // ES
-        a[: 2 * n_local].uniform_(0, 1)
-        ref_sum = float(a[: 2 * n_local].sum())
+        # ---- parity BEFORE anything is timed: index-encoded fill, every transposition and both execute
+        # directions checked element for element, on device, against the analytic pencils ----------
+        from dtfft_b200.plan import Layout
+
+        pen = [plan.get_pencil(l) for l in (Layout.X_PENCILS, Layout.Y_PENCILS, Layout.Z_PENCILS)]
+        parity = {}
+        with torch.cuda.stream(stream):
+            want = [expected_pencil(torch, pen[d], d, dims, a.device) for d in range(3)]
+
+            def step(name, fn, src, dst, d_dst):
+                dst.fill_(-7.0)  # a stale result of an earlier step must not pass
+                stream.synchronize()
+                barrier()
+                fn()
+                stream.synchronize()
+                barrier()
+                parity[name] = holds(torch, dst, want[d_dst])
+
+            encode(torch, a, want[0])
+            step("X_TO_Y", lambda: plan.transpose(a, b, Transpose.X_TO_Y, aux), a, b, 1)
+            step("Y_TO_Z", lambda: plan.transpose(b, a, Transpose.Y_TO_Z, aux), b, a, 2)
+            step("Z_TO_Y", lambda: plan.transpose(a, b, Transpose.Z_TO_Y, aux), a, b, 1)
+            step("Y_TO_X", lambda: plan.transpose(b, a, Transpose.Y_TO_X, aux), b, a, 0)
+            # the timed path: dtfft_execute (first call eager, second captured into a CUDA graph, third
+            # replayed where graphs apply) -- all three must deliver the Z pencils / return the X pencils
+            for rep in ("eager", "captured", "replayed"):
+                encode(torch, a, want[0])
+                step(f"execute_forward_{rep}", lambda: plan.execute(a, b, Execute.FORWARD, aux), a, b, 2)
+                step(f"execute_backward_{rep}", lambda: plan.execute(b, a, Execute.BACKWARD, aux), b, a, 0)
+            encode(torch, a, want[0])
+        stream.synchronize()
         torch.cuda.synchronize()
         barrier()
         for _ in range(args.warmup):
             _plan_cycle(plan, Execute, a, b, aux)
         stream.synchronize()
-        assert float(a[: 2 * n_local].sum()) == ref_sum, "cycle is not the identity"
+        with torch.cuda.stream(stream):
+            parity["after_warmup_cycles"] = holds(torch, a, want[0])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
@@ -241,11 +341,26 @@ def run_ours(args):
             stream.synchronize()
             barrier()
         ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        with torch.cuda.stream(stream):
+            parity["after_timed_cycles"] = holds(torch, a, want[0])
+        stream.synchronize()
+        del want
+        # every rank must agree on every check
+        flags = torch.tensor([1.0 if parity[k] else 0.0 for k in sorted(parity)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        parity = {k: ("bit-exact" if float(flags[i]) == 1.0 else "MISMATCH") for i, k in enumerate(sorted(parity))}
+        peer_err = plan.peer_error() if hasattr(plan, "peer_error") else 0
         results[bname] = {"plan": plan, "ms": ms, "launches": launches, "clocks": clocks.summary(), "a": a, "b": b,
                           "aux": aux, "stream": stream, "bufs": bufs + [aux_buf], "n_local": n_local,
-                          "backend": plan.backend.name}
+                          "backend": plan.backend.name, "parity": parity, "peer_error": peer_err}
         if best is None or ms < results[best]["ms"]:
             best = bname
+    bad = {k: v["parity"] for k, v in results.items() if any(x != "bit-exact" for x in v["parity"].values())}
+    if bad:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": "parity mismatch against the analytic pencils", "parity": bad}), flush=True)
+        sys.exit(1)
     R = results[best]
     plan, a, b, aux, stream, n_local = R["plan"], R["a"], R["b"], R["aux"], R["stream"], R["n_local"]
     ms_per_step = R["ms"]
@@ -270,16 +385,18 @@ def run_ours(args):
     for i, (t, _, _) in enumerate(order):
         per_type[t.name] = max_over_ranks(sum(kms[i::4]) / len(kms[i::4]))
     k_bytes = 2 * n_local * ES  # one read + one write of the local pencil
-    achieved = k_bytes / (k_avg_ms * 1e-3) / 1e9
-    remote = sum(st["remote_bytes"] for _, _, st in evs) / len(evs)
-    # NVLink accounting: only transpositions that carry an exchange (remote bytes > 0) count
+    # transpositions without an exchange are one HBM-bound kernel; those with one are NVLink-bound
+    remote_of = {t.name: max_over_ranks(evs[i][2]["remote_bytes"]) for i, (t, _, _) in enumerate(order)}
+    local_names = [nm for nm, rb in remote_of.items() if rb == 0]
+    exch_names = [nm for nm, rb in remote_of.items() if rb > 0]
+    loc_ms = sum(per_type[nm] for nm in local_names) / len(local_names) if local_names else None
+    achieved = k_bytes / (loc_ms * 1e-3) / 1e9 if loc_ms else k_bytes / (k_avg_ms * 1e-3) / 1e9
     link = {}
-    for i, (t, _, _) in enumerate(order):
-        rb = max_over_ranks(evs[i][2]["remote_bytes"])
-        if rb > 0:
-            link[t.name] = {"remote_bytes_per_gpu": rb, "ms": per_type[t.name],
-                            "GBps_per_direction": rb / (per_type[t.name] * 1e-3) / 1e9,
-                            "frac_of_900": rb / (per_type[t.name] * 1e-3) / 1e9 / 900.0}
+    for nm in exch_names:
+        rb = remote_of[nm]
+        link[nm] = {"remote_bytes_per_gpu": rb, "ms": per_type[nm],
+                    "GBps_per_direction": rb / (per_type[nm] * 1e-3) / 1e9,
+                    "frac_of_900": rb / (per_type[nm] * 1e-3) / 1e9 / 900.0}
     peak, peak_src = measured_peaks()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu capture
@@ -295,12 +412,11 @@ def run_ours(args):
     ki = probe.info()
     probe.destroy()
     tname = f"transpose_tiles_kernel<uint4,{ki['tile_a'] // 32},{ki['tile_b'] // 32},{ki['threads'] // 32}>"
-    if world == 1:
-        kernel_name = f"{tname} (one launch per transposition)"
-    elif R["backend"] == "NVLINK_FUSED":
-        kernel_name = f"{tname} with peer-mapped destinations (+2 peer_barrier_kernel)"
+    kernel_name = f"{tname} (one launch per local transposition)"
+    if R["backend"] == "NVLINK_FUSED":
+        exchange_kernel_name = f"{tname} with peer-mapped destinations (+ peer barriers)"
     else:
-        kernel_name = "transpose_tiles_kernel (pack) + ncclSend/Recv + rows_copy_kernel (unpack)"
+        exchange_kernel_name = "transpose_tiles_kernel (pack) + ncclSend/Recv + rows_copy_kernel (unpack)"
 
     # ---- end to end with host buffers (H2D + cycle + D2H inside the timed region) -----------
     # Every step copies ITS input pencil from pinned host memory to the device, runs the cycle
@@ -377,23 +493,47 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_cycle_times(256, 1)
-            t256, threads = cpu_cycle_times(256, 3)
-            t512, _ = cpu_cycle_times(n, 1)
+            block, table = cpu_pick_variant(256)
+            variant = "unblocked" if block == 0 else f"block_{block}"
+            cpu_cycle_times(n, 1, block)  # warm-up at full size (page faults)
+            t512, threads = cpu_cycle_times(n, 2, block)
             tt = min(t512)
             cpu = {"value": CYCLE_BYTES / tt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": "1 full 512^3 c128 cycle (4 permutes) after a 256^3 warm-up; oracle C/OpenMP port of the reference host kernels",
-                   "ms_per_step": tt * 1e3, "ms_per_step_256": min(t256) * 1e3}
+                   "sample": f"2 full 512^3 c128 cycles (4 permutes each) after 1 warm-up cycle, best of 2; oracle C/OpenMP port of the "
+                             f"reference host kernels, variant {variant} = fastest of unblocked / block 4..64 on a 256^3 sample "
+                             "(the reference's host kernel autotunes the same set)",
+                   "ms_per_step": tt * 1e3, "variant": variant, "variant_ms_on_256^3": table}
         except Exception as ex:  # the baseline is reported, never a gate
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
     grid = plan.grid_dims
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": kernel_name, "bytes_per_launch": k_bytes,
+                "avg_launch_ms": loc_ms if loc_ms else k_avg_ms, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    if world > 1:
+        # N > 1: the cycle has two kinds of transposition with two different roofs; the top-level fields
+        # describe the local (HBM-bound) kernel, `exchange` the NVLink-bound one -- never a blend
+        roofline["scope"] = ("local transpositions only (" + ", ".join(local_names) + ")") if local_names else \
+            "every transposition exchanges: HBM figure = whole transposition incl. its exchange"
+        roofline["local"] = {"bound": "hbm", "kernel": f"{tname} (one launch, no exchange)", "transpositions": local_names,
+                             "bytes_per_launch": k_bytes, "avg_launch_ms": loc_ms, "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak} if local_names else None
+        ex_bytes = sum(v["remote_bytes_per_gpu"] for v in link.values())
+        ex_ms = sum(v["ms"] for v in link.values())
+        ach = ex_bytes / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else 0.0
+        roofline["exchange"] = {"bound": "nvlink", "kernel": exchange_kernel_name, "transpositions": exch_names,
+                                "bytes_out_per_launch_per_gpu": ex_bytes / max(1, len(link)),
+                                "avg_launch_ms": ex_ms / max(1, len(link)), "achieved": ach, "peak": 900.0,
+                                "unit": "GB/s per direction per GPU", "frac": ach / 900.0,
+                                "frac_of_measured_dma_737": ach / 737.0,
+                                "note": "remote payload / whole transposition time (device barriers + local tiles + remote "
+                                        "stores); 737 GB/s = cudaMemcpyPeerAsync on this pool (profiles/r01c_p2p_n8.json)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128 (opaque 16-byte moves)", "data": "synthetic",
-        "config": {"workload": f"3D C2C fp64 512^3 transpose-only pencil cycle X->Y->Z->Y->X on {world} B200 "
-                               "(BASELINE configs[1]) through dtfft_execute FORWARD + BACKWARD",
+        "config": {"workload": WORKLOAD.format(world=world),
                    "global_dims": dims, "grid": grid, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
                    "backend": R["backend"], "transposition_ms": per_type,
                    "switches": {k: os.environ[k] for k in ("DTFFTB_TRANSPOSE_OVERLAP", "DTFFTB_FUSED_SYNC", "DTFFTB_CACHE_HINT",
@@ -402,9 +542,12 @@ def run_ours(args):
                    "l2": f"working set 2 x {n_local * ES / 2**20:.0f} MiB per transposition per GPU >> 126 MB L2 (no flush needed)"
                    if n_local * ES > 2**28 else
                    f"working set {3 * n_local * ES / 2**20:.0f} MiB over 3 buffers per GPU cycles through L2 (126 MB); buffers alternate so no transposition re-reads what the previous one wrote from L2 alone"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": kernel_name, "bytes_per_launch": k_bytes,
-                     "avg_launch_ms": k_avg_ms, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "roofline": roofline,
+        "parity": {"checked": "every element of every rank, on device, against the analytic X/Y/Z pencils of the "
+                              "index-encoded global array (= the reference's host MPI-datatype path), before the timed region; "
+                              "the round trip again after the warm-up and after the timed cycles",
+                   "per_backend": {k: v["parity"] for k, v in results.items()},
+                   "peer_error": {k: v["peer_error"] for k, v in results.items()}},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n_local * ES * world,
                 "d2h_bytes_per_step": n_local * ES * world, "steps": e2e_steps,
@@ -416,13 +559,8 @@ def run_ours(args):
     }
     if world > 1:
         ex_bytes = sum(v["remote_bytes_per_gpu"] for v in link.values())
-        ex_ms = sum(v["ms"] for v in link.values())
-        ach = ex_bytes / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else 0.0
-        line["nvlink"] = {"per_exchange_transposition": link, "achieved": ach, "peak": 900.0,
-                          "unit": "GB/s per direction per GPU", "frac": ach / 900.0,
-                          "bytes_out_per_cycle_per_gpu": 2 * ex_bytes,
-                          "note": "remote payload of the transpositions that exchange / their whole time "
-                                  "(device barriers + local tiles + remote stores); local-only transpositions excluded"}
+        line["nvlink"] = dict(roofline["exchange"], per_exchange_transposition=link,
+                              bytes_out_per_cycle_per_gpu=ex_bytes)
     for v in results.values():
         for x in v["bufs"]:
             v["plan"].mem_free(x)

@@ -23,6 +23,10 @@ class DtfftB200Error(RuntimeError):
 
 
 def describe_error(code: int) -> str:
+    named = {-30001: "NVLINK_FUSED: `out` is not a registered buffer", -30002: "host allgather callback failed",
+             -30003: "NVLINK_FUSED: a peer missed a device barrier (time-out); the plan is dead"}
+    if code in named:
+        return named[code]
     if code <= -30000:
         return "internal invariant violated"
     if code <= -20000:
@@ -75,6 +79,9 @@ def lib() -> C.CDLL:
     L.dtfftb_kernel_get_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 5 + [i64p]
     L.dtfftb_kernel_set_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.dtfftb_kernel_autotune.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.dtfftb_kernel_autotune_report.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), i32p,
+                                                C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    L.dtfftb_kernel_autotune_report.restype = C.c_int
     L.dtfftb_kernel_create_dry.argtypes = [C.POINTER(vp), C.c_int, i32p, C.c_int, C.c_int64, i32p, C.c_int]
     L.dtfftb_kernel_create_boxes_dry.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.c_int, i64p, C.c_int]
     L.dtfftb_kernel_dump_table.argtypes = [vp, C.c_int, C.c_int, C.c_int32, i64p, i32p, i64p, i32p]

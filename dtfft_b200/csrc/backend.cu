@@ -70,15 +70,17 @@ int NcclBackend::execute(void* in, void* out, cudaStream_t stream, void* aux) {
         const int rnk = mapping_[i];
         if (sfloats_[i] > 0) {
             nr = ncclSend(pin + sdispl_[i], (size_t)sfloats_[i], ncclFloat, rnk, nccl_, stream);
-            if (nr != ncclSuccess) return nccl_error(nr);
+            if (nr != ncclSuccess) break;
         }
         if (rfloats_[i] > 0) {
             nr = ncclRecv(pout + rdispl_[i], (size_t)rfloats_[i], ncclFloat, rnk, nccl_, stream);
-            if (nr != ncclSuccess) return nccl_error(nr);
+            if (nr != ncclSuccess) break;
         }
     }
-    nr = ncclGroupEnd();
+    // the group is closed on the error path too: an open group would swallow every later NCCL call
+    const ncclResult_t ne = ncclGroupEnd();
     if (nr != ncclSuccess) return nccl_error(nr);
+    if (ne != ncclSuccess) return nccl_error(ne);
     if (pipelined_) {  // :126-132
         for (int i = 0; i < P_; ++i) {
             if (rfloats_[i] > 0 && unpack_) {

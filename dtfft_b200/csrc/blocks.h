@@ -48,6 +48,7 @@ struct BlockDesc {
     long long os0, os1, os2;  // output strides of axes a, b, c (family R: os0 == 1)
     long long item_begin; // first work item of this block in the flattened item space
     long long shuffle;    // blocks[0] only: > 1 -> CTA i works on item (i * shuffle) mod total (coprime multiplier)
+    const unsigned long long* abort;  // blocks[0] only: non-null -> sticky peer-error word; when set the kernel stores nothing
     int n0, n1, n2;       // extents along a, b, c
     int tiles0, tiles1;   // tiles along a and b
     FastDiv div0, div1;   // fast division by tiles0 / tiles1
@@ -69,7 +70,8 @@ struct FusedSync {
     unsigned long long* epoch_free;         // group epoch counters of the two channels
     unsigned long long* epoch_landed;
     unsigned int* tickets;                  // [0] CTAs that entered, [1] CTAs that finished
-    unsigned long long* err;                // sticky error word (time-out)
+    unsigned long long* err;                // sticky error word (time-out), device memory: read by the kernels
+    unsigned long long* err_host;           // its mirror in mapped host memory: read by the API without a sync
     long long timeout_cycles;
 };
 

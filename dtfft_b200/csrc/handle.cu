@@ -182,6 +182,7 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
         std::unique_ptr<Kernel> k(new Kernel);
         rc = k->create_boxes(fused_family_, es_, fused_boxes_);
         if (rc) return rc;
+        k->set_abort_flag(peers.abort_flag());
         rc = k->set_peer_out(bases.data(), nullptr);
         if (rc) return rc;
         if (fused_.size() >= kMaxCachedDestinations) forget_buffers();
@@ -233,6 +234,7 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
             ks[(size_t)c].reset(new Kernel);
             rc = ks[(size_t)c]->create_boxes(fused_family_, es_, boxes);
             if (rc) return rc;
+            ks[(size_t)c]->set_abort_flag(ctx_.peers->abort_flag());
             rc = ks[(size_t)c]->set_peer_out(bases.data(), nullptr);
             if (rc) return rc;
         }

@@ -149,4 +149,21 @@ int dtfftb_kernel_autotune(dtfftb_kernel_t kernel, const void* in, void* out, vo
     return kernel->k.autotune(in, out, static_cast<cudaStream_t>(stream), n_warmup, n_iters, best_ms);
 }
 
+int dtfftb_kernel_autotune_report(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
+                                  int n_iters, int max_entries, int* n_entries, int32_t* tiles, float* ms, double* gbs) {
+    if (!kernel || !n_entries || max_entries < 0) return DTFFT_ERROR_INVALID_USAGE;
+    std::vector<dtfftb::Kernel::AutotuneEntry> log;
+    kernel->k.set_autotune_log(&log);
+    float best = 0.f;
+    const int rc = kernel->k.autotune(in, out, static_cast<cudaStream_t>(stream), n_warmup, n_iters, &best);
+    kernel->k.set_autotune_log(nullptr);
+    *n_entries = (int)log.size();
+    for (int i = 0; i < (int)log.size() && i < max_entries; ++i) {
+        if (tiles) tiles[3 * i] = 32 * log[(size_t)i].cfg.ka, tiles[3 * i + 1] = 32 * log[(size_t)i].cfg.kb, tiles[3 * i + 2] = 32 * log[(size_t)i].cfg.rows;
+        if (ms) ms[i] = log[(size_t)i].ms;
+        if (gbs) gbs[i] = log[(size_t)i].gbs;
+    }
+    return rc;
+}
+
 }  // extern "C"

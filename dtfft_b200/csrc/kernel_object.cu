@@ -520,6 +520,13 @@ int Kernel::rebuild_tables() {
             host[(size_t)t.offset].shuffle = s;
         }
     }
+    if (abort_flag_) {  // the first block of every table a launch can start from
+        for (int slot = 0; slot < 3; ++slot) {
+            if (all_[slot].nblocks > 0) host[(size_t)all_[slot].offset].abort = abort_flag_;
+            for (const DeviceTable& t : single_[slot])
+                if (t.nblocks > 0) host[(size_t)t.offset].abort = abort_flag_;
+        }
+    }
     if (dry_) {
         host_tables_ = host;
         return DTFFT_SUCCESS;
@@ -574,6 +581,12 @@ int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cu
     cudaError_t ce;
     const int cap = grid_limit_ > 0 ? std::min(grid_cap_, grid_limit_) : grid_cap_;
     if (family_ == FAM_T) {
+        // family T moves whole elements with es_-wide accesses: every base it touches must be aligned
+        // to the element size (family R narrows its unit instead, pick_unit)
+        const uintptr_t mask = (uintptr_t)es_ - 1;
+        if ((reinterpret_cast<uintptr_t>(in) & mask) || (reinterpret_cast<uintptr_t>(out) & mask)) return DTFFT_ERROR_INVALID_USAGE;
+        for (void* p : peer_out_)
+            if (reinterpret_cast<uintptr_t>(p) & mask) return DTFFT_ERROR_INVALID_USAGE;
         ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream, sync);
     } else {
         const int slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
@@ -605,10 +618,7 @@ int Kernel::execute(const void* in, void* out, cudaStream_t stream, int neighbor
     } else {
         int unit = (int)es_;
         int slot = 0;
-        if (family_ == FAM_T) {
-            if (reinterpret_cast<uintptr_t>(in) % es_ || reinterpret_cast<uintptr_t>(out) % es_)
-                return DTFFT_ERROR_INVALID_USAGE;
-        } else {
+        if (family_ != FAM_T) {  // family T: alignment is checked in launch()
             unit = pick_unit(in, out);
             slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
         }
@@ -701,9 +711,10 @@ int Kernel::autotune(const void* in, void* out, cudaStream_t stream, int n_warmu
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         ms /= std::max(1, n_iters);
-        if (getenv("DTFFTB_LOG"))
-            fprintf(stderr, "[dtfftb] autotune es=%d tile=%dx%d rows=%d: %.4f ms\n", (int)es_, 32 * c.ka, 32 * c.kb,
-                    c.rows, ms);
+        if (getenv("DTFFTB_LOG"))  // kernel_device.F90:385-389 prints time and bandwidth of every candidate
+            fprintf(stderr, "[dtfftb] autotune es=%d tile=%dx%d rows=%d: %.4f ms, %.1f GB/s\n", (int)es_, 32 * c.ka,
+                    32 * c.kb, c.rows, ms, ms > 0 ? 2.0 * (double)bytes_moved() / (ms * 1e-3) / 1e9 : 0.0);
+        if (autotune_log_) autotune_log_->push_back(AutotuneEntry{c, ms, ms > 0 ? 2.0 * (double)bytes_moved() / (ms * 1e-3) / 1e9 : 0.0});
         if (ms < best) best = ms, best_cfg = c;
     }
     cudaEventDestroy(e0);

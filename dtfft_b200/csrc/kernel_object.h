@@ -72,8 +72,18 @@ public:
     // Run as a persistent kernel of at most `max_ctas` CTAs (0 = no limit).  Used when the launch
     // shares the GPU with another stream (stage overlap): the NVLink-bound stores need few SMs.
     void set_grid_limit(int max_ctas) { grid_limit_ = max_ctas; }
+    // Fused NVLink kernels: device address of the group's sticky peer-error word (peer.h).  Takes effect at
+    // the next table rebuild (set_peer_out / set_tile); once the word is set the kernel stores nothing.
+    void set_abort_flag(const unsigned long long* flag) { abort_flag_ = flag; }
     int sm_count() const { return sm_count_; }
     int autotune(const void* in, void* out, cudaStream_t stream, int n_warmup, int n_iters, float* best_ms);
+    // One entry per tile candidate the last autotune() timed (kernel_device.F90:385-389 logs the same pair).
+    struct AutotuneEntry {
+        TileCfg cfg;
+        float ms;
+        double gbs;  // 2 x bytes moved / time
+    };
+    void set_autotune_log(std::vector<AutotuneEntry>* log) { autotune_log_ = log; }
     void destroy();
 
     // Host-only mode (tests on CPU boxes): geometry and tables are built exactly as for a launch but
@@ -112,6 +122,8 @@ private:
     std::vector<void*> peer_out_; // optional per-neighbour out base
     std::vector<long long> peer_out_displ_;
     TileCfg tile_{1, 1, 8};
+    std::vector<AutotuneEntry>* autotune_log_ = nullptr;
+    const unsigned long long* abort_flag_ = nullptr;
     int tx_ = 32;
     int tx_slot_[3] = {32, 32, 32};
     int unit_geo_ = 4;  // widest unit the geometry allows (family R)

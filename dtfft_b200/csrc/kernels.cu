@@ -22,6 +22,8 @@ namespace dtfftb {
 
 namespace {
 
+constexpr int kMaxDevices = 64;
+
 template <int ES> struct ElemT;
 template <> struct ElemT<4> { using type = unsigned int; };
 template <> struct ElemT<8> { using type = uint2; };
@@ -129,8 +131,10 @@ __device__ __forceinline__ void sync_wait_flag(const unsigned long long* flag, u
     for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         if (v >= epoch) break;
-        if (clock64() - t0 > s->timeout_cycles) {
-            *s->err = 1;
+        if (clock64() - t0 > s->timeout_cycles) {  // fatal: see peer_barrier_kernel
+            *reinterpret_cast<volatile unsigned long long*>(s->err) = 1;
+            *reinterpret_cast<volatile unsigned long long*>(s->err_host) = 1;
+            __threadfence_system();
             break;
         }
         __nanosleep(64);
@@ -183,6 +187,19 @@ __device__ __forceinline__ void fused_sync_leave(const FusedSync* __restrict__ s
     }
 }
 
+// Fused NVLink tables carry the address of the sticky peer-error word (blocks.h: BlockDesc::abort).  Once
+// a device barrier has timed out the destination was never announced free (or blocks never landed):
+// every later kernel of the group stores nothing, and the next API call returns
+// DTFFTB_ERROR_PEER_TIMEOUT.  One read per CTA, shared so that the whole CTA takes the same branch.
+__device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks, int t) {
+    const unsigned long long* flag = blocks[0].abort;
+    if (!flag) return false;
+    __shared__ unsigned s_abort;
+    if (t == 0) s_abort = *reinterpret_cast<const volatile unsigned long long*>(flag) != 0ull ? 1u : 0u;
+    __syncthreads();
+    return s_abort != 0u;
+}
+
 // ---------------------------------------------------------------------------------
 // Family T
 // ---------------------------------------------------------------------------------
@@ -199,12 +216,13 @@ __global__ void __launch_bounds__(32 * ROWS)
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     if constexpr (SYNC) fused_sync_enter(sync);
+    const bool aborted = peer_abort(blocks, ty * 32 + tx);
 
     // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
     // item space, so remote (NVLink-bound) and local (HBM-bound) tiles overlap instead of running
     // one peer after the other, and no peer sees the traffic of every rank at once.
     const long long shuffle = __ldg(&blocks[0].shuffle);
-    for (long long it0 = blockIdx.x; it0 < total_items; it0 += gridDim.x) {
+    for (long long it0 = blockIdx.x; it0 < total_items && !aborted; it0 += gridDim.x) {
         const long long item = shuffle > 1 ? (it0 * shuffle) % total_items : it0;
         const int bi = find_block(blocks, nblocks, item);
         const BlockDesc& d = blocks[bi];
@@ -259,13 +277,18 @@ cudaError_t launch_T_hint(const void* in, void* out, const BlockDesc* blocks, in
     constexpr size_t smem = (size_t)(32 * KA) * (32 * KB + 1) * ES;
     auto kern = transpose_tiles_kernel<T, KA, KB, ROWS, HINT, SYNC>;
     if (smem > 48 * 1024) {
-        static bool attr_set = false;  // per instantiation
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // function attributes are per device: one flag per (instantiation, device)
+        static bool attr_set[kMaxDevices] = {};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kMaxDevices || !attr_set[dev]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             // let three 66.5 KB tiles share an SM
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            attr_set = true;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < kMaxDevices) attr_set[dev] = true;
         }
     }
     long long g = total < grid_cap ? total : grid_cap;
@@ -315,12 +338,13 @@ __global__ void __launch_bounds__(kRowsThreads)
     constexpr int UR = kRowsPerThread;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     if constexpr (SYNC) fused_sync_enter(sync);
+    const bool aborted = peer_abort(blocks, (int)threadIdx.x);
 
     // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
     // item space, so remote (NVLink-bound) and local (HBM-bound) tiles overlap instead of running
     // one peer after the other, and no peer sees the traffic of every rank at once.
     const long long shuffle = __ldg(&blocks[0].shuffle);
-    for (long long it0 = blockIdx.x; it0 < total_items; it0 += gridDim.x) {
+    for (long long it0 = blockIdx.x; it0 < total_items && !aborted; it0 += gridDim.x) {
         const long long item = shuffle > 1 ? (it0 * shuffle) % total_items : it0;
         const int bi = find_block(blocks, nblocks, item);
         const BlockDesc& d = blocks[bi];

@@ -3,6 +3,7 @@
 
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,7 +93,7 @@ void ipc_close(void* p) {
 __global__ void peer_barrier_kernel(uint64_t* const* __restrict__ peer_flags, uint64_t* __restrict__ my_flags,
                                     const int* __restrict__ members, int n, int me, size_t row,
                                     uint64_t* __restrict__ epoch_counter, long long timeout_cycles,
-                                    uint64_t* __restrict__ err) {
+                                    uint64_t* __restrict__ err, uint64_t* __restrict__ err_host) {
     __shared__ uint64_t s_epoch;
     const int t = threadIdx.x;
     if (t == 0) {
@@ -112,8 +113,10 @@ __global__ void peer_barrier_kernel(uint64_t* const* __restrict__ peer_flags, ui
     for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
         if (v >= epoch) break;
-        if (clock64() - t0 > timeout_cycles) {
-            *err = 1;
+        if (clock64() - t0 > timeout_cycles) {  // fatal: later kernels store nothing, the next API call fails
+            *reinterpret_cast<volatile uint64_t*>(err) = 1;
+            *reinterpret_cast<volatile uint64_t*>(err_host) = 1;
+            __threadfence_system();
             break;
         }
         __nanosleep(64);
@@ -159,6 +162,19 @@ int PeerRegistry::init(const Comm& world) {
         available_ = true;
         return DTFFT_SUCCESS;
     }
+    {  // time-out of the device barriers: DTFFTB_PEER_TIMEOUT_MS milliseconds at the SM clock
+        long long ms = 20000;
+        if (const char* e = getenv("DTFFTB_PEER_TIMEOUT_MS")) ms = std::max(1ll, atoll(e));
+        int khz = 2000000;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, me.device) != cudaSuccess || khz <= 0) khz = 2000000;
+        cudaGetLastError();
+        timeout_cycles_ = ms * (long long)khz;
+    }
+    ce = cudaHostAlloc(reinterpret_cast<void**>(&h_err_), sizeof(uint64_t), cudaHostAllocMapped);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    *h_err_ = 0;
+    ce = cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_err_host_), h_err_, 0);
+    if (ce != cudaSuccess) return cuda_error(ce);
     const size_t n = (size_t)kChannels * P + 8;
     ce = cudaMalloc(&flags_, n * sizeof(uint64_t));
     if (ce != cudaSuccess) return cuda_error(ce);
@@ -321,7 +337,8 @@ const FusedSync* PeerRegistry::fused_sync(const std::vector<int>& members, int c
     h.epoch_landed = reinterpret_cast<unsigned long long*>(gl->d_epoch);
     h.tickets = e.d_tickets;
     h.err = reinterpret_cast<unsigned long long*>(flags_ + (size_t)kChannels * P);
-    h.timeout_cycles = 40ll * 1000 * 1000 * 1000;  // as barrier(): ~20 s, then a sticky error instead of a hung GPU
+    h.err_host = reinterpret_cast<unsigned long long*>(d_err_host_);
+    h.timeout_cycles = timeout_cycles_;  // as barrier(): then a sticky, fatal error instead of a hung GPU
     cudaMemcpy(e.d_state, &h, sizeof(h), cudaMemcpyHostToDevice);
     syncs_.emplace(key, e);
     return e.d_state;
@@ -346,11 +363,10 @@ int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStre
     Group& g = *gp;
     const int P = world_.size();
     uint64_t* err = flags_ + (size_t)kChannels * P;
-    // ~20 s at 2 GHz: a missing peer turns into a sticky error instead of a hung GPU
-    const long long timeout = 40ll * 1000 * 1000 * 1000;
+    // a missing or late peer turns into a sticky, fatal error instead of a hung GPU
     const int threads = ((n + 31) / 32) * 32;
     peer_barrier_kernel<<<1, threads, 0, stream>>>(g.d_peer_flags, flags_, g.d_members, n, world_.rank(),
-                                                   (size_t)channel * P, g.d_epoch, timeout, err);
+                                                   (size_t)channel * P, g.d_epoch, timeout_cycles_, err, d_err_host_);
     cudaError_t ce = cudaGetLastError();
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
@@ -375,11 +391,9 @@ int PeerRegistry::reset_barriers() {
     return DTFFT_SUCCESS;
 }
 
-int PeerRegistry::error_state() {
-    if (!flags_) return 0;
-    uint64_t v = 0;
-    cudaMemcpy(&v, flags_ + (size_t)kChannels * world_.size(), sizeof(v), cudaMemcpyDeviceToHost);
-    return (int)v;
+int PeerRegistry::error_state() const {
+    if (!h_err_) return 0;
+    return (int)*reinterpret_cast<volatile const uint64_t*>(h_err_);
 }
 
 void PeerRegistry::destroy() {
@@ -406,6 +420,9 @@ void PeerRegistry::destroy() {
     if (flags_) cudaFree(flags_);
     flags_ = nullptr;
     flags_slot_ = -1;
+    if (h_err_) cudaFreeHost(h_err_);
+    h_err_ = nullptr;
+    d_err_host_ = nullptr;
     cudaGetLastError();
     inited_ = false;
     available_ = false;

@@ -54,8 +54,14 @@ public:
     // communicators change (process-grid search), because a new group starts at epoch 0 while the
     // flag rows of its channel may still hold the last epoch of a differently composed group.
     int reset_barriers();
-    // Non-zero if a barrier ever timed out (peer missing); sticky.
-    int error_state();
+    // Non-zero if a barrier ever timed out (peer missing or late); sticky.  Reads a word in mapped host
+    // memory that the timed-out kernel wrote: no synchronisation, cheap enough for every API call.
+    int error_state() const;
+    // Device address of the sticky error word; the fused kernels poll it and store nothing once it is set.
+    const unsigned long long* abort_flag() const {
+        return flags_ ? reinterpret_cast<const unsigned long long*>(flags_ + (size_t)kChannels * world_.size()) : nullptr;
+    }
+    long long timeout_cycles() const { return timeout_cycles_; }
     void destroy();
 
     static constexpr int kChannels = 10;
@@ -88,6 +94,9 @@ private:
     const char* why_ = "not initialised";
     std::vector<Slot> slots_;
     uint64_t* flags_ = nullptr;  // [kChannels][world] + error word
+    uint64_t* h_err_ = nullptr;  // mirror of the error word in mapped pinned host memory
+    uint64_t* d_err_host_ = nullptr;  // device address of h_err_
+    long long timeout_cycles_ = 40ll * 1000 * 1000 * 1000;  // DTFFTB_PEER_TIMEOUT_MS (default 20 s) x SM clock
     int flags_slot_ = -1;
     std::map<std::pair<int, std::vector<int>>, Group> groups_;
 };

@@ -656,7 +656,10 @@ int Plan::time_backend(int backend, double* ms, bool reshapes) {
     rc = mem_alloc(bytes, &a);
     if (!rc) rc = mem_alloc(bytes, &b);
     if (!rc && aux) rc = mem_alloc(aux, &w);
-    if (!rc) {
+    // every rank must take the same branch: the timed branch ends in a collective max
+    const bool all_ok = comm_.sum(rc == DTFFT_SUCCESS ? 1 : 0) == comm_.size();
+    if (!all_ok && !rc) rc = DTFFT_ERROR_ALLOC_FAILED;
+    if (all_ok) {
         cudaMemsetAsync(a, 0, bytes, stream_);
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0), cudaEventCreate(&e1);
@@ -1005,20 +1008,26 @@ int Plan::mem_alloc(size_t bytes, void** ptr) {
     *ptr = nullptr;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
     if (bytes == 0) return DTFFT_ERROR_INVALID_ALLOC_BYTES;
+    const bool fused = backend_ == BACKEND_NVLINK_FUSED || reshape_backend_ == BACKEND_NVLINK_FUSED;
+    // With the fused backend the registration below is collective (an allgather of IPC handles): a rank whose
+    // allocation fails must not leave the others waiting in it.  The local outcome is agreed on first and
+    // every rank backs out together.
+    const bool collective = fused && comm_.size() > 1 && peers_.available();
+    int local_rc = DTFFT_SUCCESS;
     {  // reshape_plan_base.F90:412, 429-432: refuse what cannot fit instead of letting the allocator fail
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-            if (bytes > free_b) return DTFFT_ERROR_ALLOC_FAILED;
+            if (bytes > free_b) local_rc = DTFFT_ERROR_ALLOC_FAILED;
         } else {
             cudaGetLastError();
         }
     }
+    if (local_rc && !collective) return local_rc;
     Alloc a{};
     a.bytes = bytes;
-    const bool fused = backend_ == BACKEND_NVLINK_FUSED || reshape_backend_ == BACKEND_NVLINK_FUSED;
     const bool use_nccl_alloc = nccl_ && !fused && (backend_ == BACKEND_NCCL || backend_ == BACKEND_NCCL_PIPELINED) &&
                                 getenv("DTFFTB_NO_NCCL_MEM") == nullptr;
-    if (use_nccl_alloc) {
+    if (use_nccl_alloc && !local_rc) {
         if (ncclMemAlloc(&a.ptr, bytes) == ncclSuccess) {
             a.nccl = true;
             if (ncclCommRegister(nccl_, a.ptr, bytes, &a.reg) != ncclSuccess) a.reg = nullptr;
@@ -1026,18 +1035,26 @@ int Plan::mem_alloc(size_t bytes, void** ptr) {
             a.ptr = nullptr;
         }
     }
-    if (!a.ptr) {
+    if (!a.ptr && !local_rc) {
         cudaError_t ce = cudaMalloc(&a.ptr, bytes);
         if (ce != cudaSuccess) {
             cudaGetLastError();
-            return DTFFT_ERROR_ALLOC_FAILED;
+            a.ptr = nullptr;
+            local_rc = DTFFT_ERROR_ALLOC_FAILED;
         }
     }
-    if (fused && comm_.size() > 1 && peers_.available()) {
+    if (collective) {
+        if (comm_.sum(local_rc == DTFFT_SUCCESS ? 1 : 0) != comm_.size()) {
+            if (a.ptr) cudaFree(a.ptr);
+            cudaGetLastError();
+            return DTFFT_ERROR_ALLOC_FAILED;
+        }
         int slot = -1;
         int rc = peers_.register_buffer(a.ptr, bytes, &slot);
         if (rc) return rc;
         a.peer = slot >= 0;
+    } else if (local_rc) {
+        return local_rc;
     }
     allocs_.push_back(a);
     *ptr = a.ptr;
@@ -1058,7 +1075,8 @@ int Plan::mem_free(void* ptr) {
             cudaGetLastError();
             return DTFFT_ERROR_FREE_FAILED;
         }
-        return DTFFT_SUCCESS;
+        // the memory is gone either way; tell the caller if the plan died of a peer time-out
+        return peers_.error_state() ? DTFFTB_ERROR_PEER_TIMEOUT : DTFFT_SUCCESS;
     }
     return DTFFT_ERROR_FREE_FAILED;
 }
@@ -1369,6 +1387,7 @@ int Plan::transpose(void* in, void* out, int ttype, void* aux) {
     TraceRange trace_api("dtfft_transpose", kColorTranspose);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (peers_.error_state()) return DTFFTB_ERROR_PEER_TIMEOUT;  // a device barrier timed out earlier: results are void
     const int at = std::abs(ttype);
     if (at < 1 || at > 3 || (ndims_ == 2 && at > 1) || (at == 3 && !is_z_slab_)) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
     if (in == out) return DTFFT_ERROR_INPLACE_TRANSPOSE;
@@ -1389,6 +1408,7 @@ int Plan::reshape(void* in, void* out, int rtype, void* aux) {
     TraceRange trace_api("dtfft_reshape", kColorTranspose);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (peers_.error_state()) return DTFFTB_ERROR_PEER_TIMEOUT;  // a device barrier timed out earlier: results are void
     if (!is_reshape_enabled_) return DTFFT_ERROR_RESHAPE_NOT_SUPPORTED;
     if (rtype < R_X_BRICKS_TO_PENCILS || rtype > R_Z_BRICKS_TO_PENCILS) return DTFFT_ERROR_INVALID_RESHAPE_TYPE;
     if (in == out) return DTFFT_ERROR_INPLACE_RESHAPE;
@@ -1409,6 +1429,7 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     TraceRange trace_api("dtfft_execute", kColorExecute);
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
+    if (peers_.error_state()) return DTFFTB_ERROR_PEER_TIMEOUT;  // a device barrier timed out earlier: results are void
     if (execute_type != DTFFT_EXECUTE_FORWARD && execute_type != DTFFT_EXECUTE_BACKWARD) return DTFFT_ERROR_INVALID_EXECUTE_TYPE;
     const bool inplace = in == out;
     if (is_transpose_plan_ && inplace &&

@@ -153,6 +153,21 @@ class Kernel:
                                                      n_iters, C.byref(ms)), "dtfftb_kernel_autotune")
         return float(ms.value)
 
+    def autotune_report(self, inbuf, outbuf, stream=None, n_warmup=2, n_iters=5) -> list:
+        """Timed tile autotune with the per-candidate log of the reference
+        (src/dtfft_kernel_device.F90:385-389): [{"tile_a", "tile_b", "threads", "ms", "gbs"}, ...]; the
+        fastest candidate is kept."""
+        cap = 32
+        n = C.c_int(0)
+        tiles = (C.c_int32 * (3 * cap))()
+        ms = (C.c_float * cap)()
+        gbs = (C.c_double * cap)()
+        _lib.check(_lib.lib().dtfftb_kernel_autotune_report(self._h, _ptr(inbuf), _ptr(outbuf), _stream(stream), n_warmup,
+                                                            n_iters, cap, C.byref(n), tiles, ms, gbs),
+                   "dtfftb_kernel_autotune_report")
+        return [{"tile_a": tiles[3 * i], "tile_b": tiles[3 * i + 1], "threads": tiles[3 * i + 2], "ms": float(ms[i]),
+                 "gbs": float(gbs[i])} for i in range(min(n.value, cap))]
+
     def info(self) -> dict:
         fam, unit, ta, tb, thr = (C.c_int(0) for _ in range(5))
         items = C.c_int64(0)

@@ -27,6 +27,9 @@ extern "C" {
 #define DTFFTB_ERROR_INTERNAL (-30000) /* invariant violated (reference: INTERNAL_ERROR) */
 #define DTFFTB_ERROR_NOT_REGISTERED (-30001) /* NVLINK_FUSED backend: `out` is not a registered (dtfft_mem_alloc) buffer */
 #define DTFFTB_ERROR_COMM (-30002) /* the host allgather callback failed */
+#define DTFFTB_ERROR_PEER_TIMEOUT (-30003) /* NVLINK_FUSED backend: a group member did not reach a device barrier within
+                                            * DTFFTB_PEER_TIMEOUT_MS (default 20000): the kernels of the group stored nothing
+                                            * from then on; fatal for the plan, every later call returns this code */
 
 /* ------------------------------------------------------------------------------------
  * Process group handed to the plan layer instead of an MPI_Comm.  The reference needs its
@@ -122,6 +125,12 @@ int dtfftb_kernel_set_tile(dtfftb_kernel_t kernel, int ka, int kb, int rows);
  * reference's timed kernel autotune (src/dtfft_kernel_device.F90:338-397). Returns best ms. */
 int dtfftb_kernel_autotune(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
                            int n_iters, float* best_ms);
+/* Same, and reports every candidate it timed like the reference's log line
+ * (src/dtfft_kernel_device.F90:385-389: time and bandwidth per candidate): tiles[3*i..] = (tile_a, tile_b,
+ * threads) in elements / threads, ms[i], gbs[i] = 2 x bytes moved / time.  At most max_entries are
+ * written; *n_entries is the number of candidates timed. */
+int dtfftb_kernel_autotune_report(dtfftb_kernel_t kernel, const void* in, void* out, void* stream, int n_warmup,
+                                  int n_iters, int max_entries, int* n_entries, int32_t* tiles, float* ms, double* gbs);
 
 /* ---- host-only introspection (tests on CPU boxes; nothing here touches a device) ----------
  * A "dry" kernel builds its geometry and its device tables exactly as a real one but never

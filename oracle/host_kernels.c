@@ -1,6 +1,7 @@
 /* Oracle (TEST INFRASTRUCTURE, never linked into the product): plain-C restatement of the
  * reference's CPU kernels, src/include/_dtfft_kernel_host_routines.inc ("*_write" loops,
- * OpenMP collapse as under DTFFT_WITH_OPENMP).  Used (a) as a second checker beside the
+ * OpenMP collapse as under DTFFT_WITH_OPENMP) and of the blocked whole-pencil permutes of
+ * src/include/_dtfft_kernel_host_block_routines.inc.  Used (a) as a second checker beside the
  * numpy oracle and (b) as the CPU baseline timed by bench.py ("kind": "port": the reference
  * itself is Fortran+MPI and cannot be built in this image).  0-based indices; elements are
  * opaque 4/8/16-byte words, so every result is bit-exact.
@@ -148,6 +149,85 @@ int oracle_kernel_execute(int kernel_type, int ndims, const int32_t* dims, int e
         if (rc) return rc;
     }
     return 0;
+}
+
+/* Blocked variants of the three whole-pencil permutes, src/include/_dtfft_kernel_host_block_routines.inc
+ * ("*_write" order: the block loops and the loops inside a block run in the order of the OUTPUT axes,
+ * :100-143 forward, :204-232 backward, :290-318 backward_start; BLOCK_SIZE in {4, 8, 16, 32, 64},
+ * _dtfft_kernel_host_routines.inc:1247-1255).  The reference's host kernel picks among the unblocked
+ * loops and these by timing (kernel_host create); bench.py's CPU legs do the same. */
+#define DEFINE_BLOCKED(T, SFX)                                                                              \
+    static void permute_forward_blk_##SFX(const T* in, T* out, int64_t nx, int64_t ny, int64_t nz,          \
+                                          int64_t B) {                                                      \
+        _Pragma("omp parallel for collapse(3) schedule(static)")                                            \
+        for (int64_t xb = 0; xb < nx; xb += B)                                                              \
+            for (int64_t zb = 0; zb < nz; zb += B)                                                          \
+                for (int64_t yb = 0; yb < ny; yb += B) {                                                    \
+                    const int64_t xe = xb + B < nx ? xb + B : nx, ze = zb + B < nz ? zb + B : nz;           \
+                    const int64_t ye = yb + B < ny ? yb + B : ny;                                           \
+                    for (int64_t x = xb; x < xe; ++x)                                                       \
+                        for (int64_t z = zb; z < ze; ++z)                                                   \
+                            for (int64_t y = yb; y < ye; ++y)                                               \
+                                out[x * ny * nz + z * ny + y] = in[z * nx * ny + y * nx + x];               \
+                }                                                                                           \
+    }                                                                                                       \
+    static void permute_backward_blk_##SFX(const T* in, T* out, int64_t nx, int64_t ny, int64_t nz,         \
+                                           int64_t B) {                                                     \
+        _Pragma("omp parallel for collapse(3) schedule(static)")                                            \
+        for (int64_t yb = 0; yb < ny; yb += B)                                                              \
+            for (int64_t xb = 0; xb < nx; xb += B)                                                          \
+                for (int64_t zb = 0; zb < nz; zb += B) {                                                    \
+                    const int64_t xe = xb + B < nx ? xb + B : nx, ze = zb + B < nz ? zb + B : nz;           \
+                    const int64_t ye = yb + B < ny ? yb + B : ny;                                           \
+                    for (int64_t y = yb; y < ye; ++y)                                                       \
+                        for (int64_t x = xb; x < xe; ++x)                                                   \
+                            for (int64_t z = zb; z < ze; ++z)                                               \
+                                out[y * nz * nx + x * nz + z] = in[z * nx * ny + y * nx + x];               \
+                }                                                                                           \
+    }                                                                                                       \
+    static void permute_backward_start_blk_##SFX(const T* in, T* out, int64_t nx, int64_t ny, int64_t nz,   \
+                                                 int64_t B) {                                               \
+        _Pragma("omp parallel for collapse(3) schedule(static)")                                            \
+        for (int64_t xb = 0; xb < nx; xb += B)                                                              \
+            for (int64_t yb = 0; yb < ny; yb += B)                                                          \
+                for (int64_t zb = 0; zb < nz; zb += B) {                                                    \
+                    const int64_t xe = xb + B < nx ? xb + B : nx, ze = zb + B < nz ? zb + B : nz;           \
+                    const int64_t ye = yb + B < ny ? yb + B : ny;                                           \
+                    for (int64_t x = xb; x < xe; ++x)                                                       \
+                        for (int64_t y = yb; y < ye; ++y)                                                   \
+                            for (int64_t z = zb; z < ze; ++z)                                               \
+                                out[x * nz * ny + y * nz + z] = in[z * nx * ny + y * nx + x];               \
+                }                                                                                           \
+    }                                                                                                       \
+    static int execute_blocked_##SFX(int kt, int ndims, const int32_t* dims, const T* in, T* out,           \
+                                     int64_t B) {                                                           \
+        const int64_t nx = dims[0], ny = dims[1], nz = ndims == 3 ? dims[2] : 1;                            \
+        switch (kt) {                                                                                       \
+            case K_PERMUTE_FORWARD: permute_forward_blk_##SFX(in, out, nx, ny, nz, B); return 0;            \
+            case K_PERMUTE_BACKWARD:                                                                        \
+                if (ndims == 2) permute_forward_blk_##SFX(in, out, nx, ny, 1, B);                           \
+                else permute_backward_blk_##SFX(in, out, nx, ny, nz, B);                                    \
+                return 0;                                                                                   \
+            case K_PERMUTE_BACKWARD_START: permute_backward_start_blk_##SFX(in, out, nx, ny, nz, B);        \
+                return 0;                                                                                   \
+            default: return -1;                                                                             \
+        }                                                                                                   \
+    }
+
+DEFINE_BLOCKED(uint32_t, 4)
+DEFINE_BLOCKED(uint64_t, 8)
+DEFINE_BLOCKED(w16_t, 16)
+
+/* Whole-pencil permutes with the reference's blocked loops; block in {4, 8, 16, 32, 64}. */
+int oracle_kernel_execute_blocked(int kernel_type, int ndims, const int32_t* dims, int es, const void* in, void* out,
+                                  int block) {
+    if (block != 4 && block != 8 && block != 16 && block != 32 && block != 64) return -3;
+    for (int i = 0; i < ndims; ++i)
+        if (dims[i] == 0) return 0;
+    if (es == 4) return execute_blocked_4(kernel_type, ndims, dims, (const uint32_t*)in, (uint32_t*)out, block);
+    if (es == 8) return execute_blocked_8(kernel_type, ndims, dims, (const uint64_t*)in, (uint64_t*)out, block);
+    if (es == 16) return execute_blocked_16(kernel_type, ndims, dims, (const w16_t*)in, (w16_t*)out, block);
+    return -2;
 }
 
 int oracle_num_threads(void) {
