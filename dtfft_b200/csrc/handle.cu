@@ -14,6 +14,9 @@ void ReshapeHandle::destroy() {
     local_pieces_[1].clear();
     fused_.clear();
     fused_chunks_.clear();
+    if (ctx_.peers)
+        for (auto& kv : maps_) ctx_.peers->release(&kv.second.opened);
+    maps_.clear();
     fused_boxes_.clear();
     nccl_.reset();
     pack_.reset();
@@ -130,7 +133,7 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
         // pack-free / unpack-free shortcuts (:261-266, 479-484); DTFFTB_RESHAPE_SHORTCUTS=0 keeps
         // the three-step schedule (every rank must set it alike: aux sizes change with it)
         const char* sc = getenv("DTFFTB_RESHAPE_SHORTCUTS");
-        const bool shortcuts = !(sc && sc[0] == '0');
+        const bool shortcuts = !(sc && sc[0] == '0') && !ctx_.no_shortcuts;
         geo_.is_pack_free = shortcuts && rg.is_pack_free;
         geo_.is_unpack_free = shortcuts && rg.is_unpack_free;
         if (geo_.is_pack_free) {
@@ -164,28 +167,47 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
 int ReshapeHandle::peer_bases(void* out, std::vector<void*>* bases) {
     PeerRegistry& peers = *ctx_.peers;
     const int P = (int)members_.size();
-    int slot = -1;
-    size_t off = 0;
-    if (!peers.resolve(out, (size_t)(recv_elems_ * es_), &slot, &off)) return DTFFTB_ERROR_NOT_REGISTERED;
-    bases->resize((size_t)P);
-    for (int i = 0; i < P; ++i) (*bases)[(size_t)i] = i == me_ ? out : peers.peer_ptr(members_[(size_t)i], slot, off);
+    auto it = maps_.find(out);
+    if (it != maps_.end() && it->second.id == buffer_id(out)) {
+        *bases = it->second.bases;
+        return DTFFT_SUCCESS;
+    }
+    if (it != maps_.end()) {  // the address was re-allocated: everything cached for it is stale
+        fused_.erase(out);
+        for (auto ci = fused_chunks_.begin(); ci != fused_chunks_.end();)
+            ci = ci->first.first == out ? fused_chunks_.erase(ci) : std::next(ci);
+        peers.release(&it->second.opened);
+        maps_.erase(it);
+        ++evictions_;
+    }
+    if (maps_.size() >= kMaxCachedDestinations) forget_buffers();
+    PeerMap m;
+    std::vector<void*> mapped;
+    bool ok = false;
+    int rc = peers.publish(out, (size_t)(recv_elems_ * es_), &mapped, &m.opened, &ok);
+    if (rc) return rc;
+    if (!ok) return DTFFTB_ERROR_NOT_REGISTERED;
+    m.bases.resize((size_t)P);
+    for (int i = 0; i < P; ++i) m.bases[(size_t)i] = i == me_ ? out : mapped[(size_t)members_[(size_t)i]];
+    m.id = buffer_id(out);
+    *bases = m.bases;
+    maps_.emplace(out, std::move(m));
     return DTFFT_SUCCESS;
 }
 
 int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
     PeerRegistry& peers = *ctx_.peers;
+    std::vector<void*> bases;
+    int rc = peer_bases(out, &bases);  // collective on the first use of `out`; an identity check afterwards
+    if (rc) return rc;
     auto it = fused_.find(out);
     if (it == fused_.end()) {
-        std::vector<void*> bases;
-        int rc = peer_bases(out, &bases);
-        if (rc) return rc;
         std::unique_ptr<Kernel> k(new Kernel);
         rc = k->create_boxes(fused_family_, es_, fused_boxes_);
         if (rc) return rc;
         k->set_abort_flag(peers.abort_flag());
         rc = k->set_peer_out(bases.data(), nullptr);
         if (rc) return rc;
-        if (fused_.size() >= kMaxCachedDestinations) forget_buffers();
         it = fused_.emplace(out, std::move(k)).first;
     }
     // channel: one pair per 1-D communicator id
@@ -201,7 +223,7 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
         if (const FusedSync* sync = peers.fused_sync(members_, ch_free, ch_landed))
             return it->second->execute_all(in, out, stream, sync);
     }
-    int rc = peers.barrier(members_, ch_free, stream);  // every member's `out` is free
+    rc = peers.barrier(members_, ch_free, stream);  // every member's `out` is free
     if (rc) return rc;
     rc = it->second->execute_all(in, out, stream);
     if (rc) return rc;
@@ -210,9 +232,9 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
 
 int ReshapeHandle::fused_begin(void* out, cudaStream_t stream) {
     if (!can_chunk()) return DTFFTB_ERROR_INTERNAL;
-    int slot = -1;
-    size_t off = 0;
-    if (!ctx_.peers->resolve(out, (size_t)(recv_elems_ * es_), &slot, &off)) return DTFFTB_ERROR_NOT_REGISTERED;
+    std::vector<void*> bases;
+    int rc = peer_bases(out, &bases);
+    if (rc) return rc;
     return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1), stream);
 }
 
@@ -238,7 +260,6 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
             rc = ks[(size_t)c]->set_peer_out(bases.data(), nullptr);
             if (rc) return rc;
         }
-        if (fused_chunks_.size() >= kMaxCachedDestinations) forget_buffers();
         it = fused_chunks_.emplace(key, std::move(ks)).first;
     }
     Kernel& kern = *it->second[(size_t)k];

@@ -31,6 +31,7 @@ struct HandleContext {
     ncclComm_t nccl = nullptr;      // communicator over the whole process grid (may be null when P == 1)
     PeerRegistry* peers = nullptr;  // symmetric-buffer registry (NVLINK_FUSED)
     int effort = 0;
+    bool no_shortcuts = false;      // brick reshapes: keep the three-step schedule (no aux needed)
 };
 
 class ReshapeHandle {
@@ -57,7 +58,15 @@ public:
     void forget_buffers() {
         fused_.clear();
         fused_chunks_.clear();
+        for (auto& kv : maps_) ctx_.peers->release(&kv.second.opened);
+        maps_.clear();
         ++evictions_;
+    }
+    // Identity check of a destination used before (see peer_bases): true if `out` is unknown to this handle
+    // or still the allocation whose peer mappings are cached.
+    bool destination_current(const void* out) const {
+        auto it = maps_.find(out);
+        return it == maps_.end() || it->second.id == buffer_id(out);
     }
     // Bumped whenever cached fused kernels are destroyed: a CUDA graph captured earlier may still
     // point at their device tables and must not be replayed (Plan::execute compares the counters).
@@ -130,7 +139,17 @@ private:
     std::vector<Pencil> recv_by_member_;
     // chunk kernels keyed by (my `out` pointer, nchunks)
     std::map<std::pair<const void*, int>, std::vector<std::unique_ptr<Kernel>>> fused_chunks_;
+    // Where every member receives: the members' `out` buffers mapped into this process.  The first call with
+    // a given `out` (and the first after that address was re-allocated) is COLLECTIVE over the world
+    // communicator (PeerRegistry::publish): like every dtFFT call it must be made by all ranks alike.
+    // DTFFTB_ERROR_NOT_REGISTERED (on every rank alike) if some rank's buffer cannot be shared over cudaIpc.
     int peer_bases(void* out, std::vector<void*>* bases);
+    struct PeerMap {
+        std::vector<void*> bases;   // per member of the 1-D communicator
+        std::vector<void*> opened;  // per world rank, for release()
+        unsigned long long id = 0;  // buffer_id(out) when it was published
+    };
+    std::map<const void*, PeerMap> maps_;
 };
 
 }  // namespace dtfftb

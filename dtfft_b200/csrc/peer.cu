@@ -51,6 +51,32 @@ void* allocation_base(void* ptr) {
     return reinterpret_cast<void*>((uintptr_t)base);
 }
 
+typedef int (*cuPointerGetAttribute_t)(void* data, int attribute, unsigned long long ptr);
+
+}  // namespace
+
+// CU_POINTER_ATTRIBUTE_BUFFER_ID: unique per allocation for the life of the process, so a buffer that was
+// freed and re-allocated at the same address is told apart from the one whose peer mappings are cached.
+unsigned long long buffer_id(const void* ptr) {
+    static cuPointerGetAttribute_t fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<cuPointerGetAttribute_t>(f);
+        cudaGetLastError();
+    }
+    if (!fn || !ptr) return 0;
+    unsigned long long id = 0;
+    if (fn(&id, 7 /* CU_POINTER_ATTRIBUTE_BUFFER_ID */, (unsigned long long)(uintptr_t)ptr) != 0) return 0;
+    return id;
+}
+
+namespace {
+
 // An allocation can be opened only once per process: cache by handle bytes.
 std::map<std::string, std::pair<void*, int>>& ipc_cache() {
     static std::map<std::string, std::pair<void*, int>> c;
@@ -130,6 +156,7 @@ int PeerRegistry::init(const Comm& world) {
     world_ = world;
     inited_ = true;
     available_ = false;
+    shared_device_ = false;
     const int P = world_.size();
     RankId me{};
     gethostname(me.host, sizeof(me.host) - 1);
@@ -145,15 +172,22 @@ int PeerRegistry::init(const Comm& world) {
         if (r != world_.rank() && all[r].pid == me.pid) ok = 0, why_ = "several ranks in one process";
         if (r != world_.rank() && ok) {
             int can = 0;
-            if (all[r].device == me.device)
-                ok = 0, why_ = "two ranks share a device";
-            else if (cudaDeviceCanAccessPeer(&can, me.device, all[r].device) != cudaSuccess || !can)
+            if (all[r].device == me.device) {
+                // DTFFTB_ALLOW_SHARED_DEVICE=1 (tests on a 1-GPU box): ranks time-slice one device; cudaIpc and the
+                // spin barriers work (a spinning kernel is preempted at the end of its time slice), only slowly
+                const char* e = getenv("DTFFTB_ALLOW_SHARED_DEVICE");
+                if (e && atoi(e))
+                    shared_device_ = true;
+                else
+                    ok = 0, why_ = "two ranks share a device";
+            } else if (cudaDeviceCanAccessPeer(&can, me.device, all[r].device) != cudaSuccess || !can)
                 ok = 0, why_ = "no peer access between devices";
         }
     }
     cudaGetLastError();
     if (const char* e = getenv("DTFFTB_DISABLE_P2P"))
         if (atoi(e)) ok = 0, why_ = "disabled by DTFFTB_DISABLE_P2P";
+    shared_device_ = world_.sum(shared_device_ ? 1 : 0) > 0;  // every rank must know (Plan::create skips NCCL then)
     if (world_.sum(ok) != P) {
         if (!*why_) why_ = "a peer reported no access";
         return DTFFT_SUCCESS;
@@ -243,6 +277,55 @@ int PeerRegistry::register_buffer(void* ptr, size_t bytes, int* slot_out) {
     slots_[(size_t)slot] = s;
     if (slot_out) *slot_out = slot;
     return DTFFT_SUCCESS;
+}
+
+int PeerRegistry::publish(void* ptr, size_t bytes, std::vector<void*>* mapped, std::vector<void*>* opened, bool* ok) {
+    *ok = false;
+    mapped->clear();
+    opened->clear();
+    if (!inited_ || !available_) return DTFFT_SUCCESS;
+    const int P = world_.size();
+    mapped->assign((size_t)P, nullptr);
+    (*mapped)[(size_t)world_.rank()] = ptr;
+    if (P == 1) {
+        *ok = true;
+        return DTFFT_SUCCESS;
+    }
+    IpcMsg mine{};
+    void* base = allocation_base(ptr);
+    mine.offset = (unsigned long long)((char*)ptr - (char*)base);
+    mine.bytes = bytes;
+    mine.ok = cudaIpcGetMemHandle(&mine.handle, base) == cudaSuccess ? 1 : 0;
+    cudaGetLastError();
+    std::vector<IpcMsg> all;
+    if (world_.allgather_v(mine, all)) return DTFFTB_ERROR_COMM;
+    int good = 1;
+    for (int r = 0; r < P; ++r) good &= all[r].ok;
+    opened->assign((size_t)P, nullptr);
+    for (int r = 0; r < P && good; ++r) {
+        if (r == world_.rank()) continue;
+        void* p = ipc_open(all[r].handle);
+        if (!p) {
+            good = 0;
+            break;
+        }
+        (*opened)[(size_t)r] = p;
+        (*mapped)[(size_t)r] = (char*)p + all[r].offset;
+    }
+    if (world_.sum(good) != P) {  // every rank must agree, otherwise nobody uses the mapping
+        release(opened);
+        mapped->clear();
+        return DTFFT_SUCCESS;
+    }
+    *ok = true;
+    return DTFFT_SUCCESS;
+}
+
+void PeerRegistry::release(std::vector<void*>* opened) {
+    for (void* p : *opened)
+        if (p) ipc_close(p);
+    cudaGetLastError();
+    opened->clear();
 }
 
 int PeerRegistry::unregister_buffer(void* ptr) {

@@ -26,6 +26,9 @@
 
 namespace dtfftb {
 
+// Identity of the allocation behind a device pointer (0 if unknown): changes when the address is re-allocated.
+unsigned long long buffer_id(const void* ptr);
+
 class PeerRegistry {
 public:
     ~PeerRegistry() { destroy(); }
@@ -33,6 +36,7 @@ public:
     // the same host with peer access to every other rank's device.
     int init(const Comm& world);
     bool available() const { return available_; }
+    bool shared_device() const { return shared_device_; }  // test mode, see init()
     const char* why_unavailable() const { return why_; }
 
     // Collective, same order on every rank.  `ptr` may point inside a larger cudaMalloc
@@ -40,6 +44,14 @@ public:
     int register_buffer(void* ptr, size_t bytes, int* slot_out = nullptr);
     int unregister_buffer(void* ptr);  // collective
     bool resolve(const void* ptr, size_t bytes, int* slot, size_t* offset) const;
+    // Collective over `world`, ANY device buffer (the drop-in case: the reference accepts every device
+    // pointer, src/dtfft_plan.F90:1769-1795).  Every rank publishes the buffer it is about to receive into;
+    // on return (*mapped)[r] is rank r's buffer in THIS process' address space (mine = ptr) and `opened`
+    // holds what release() must close.  *ok == false (on every rank alike) when some rank could not export
+    // its buffer through cudaIpc (stream-ordered or virtual-memory allocations) or could not map a peer's:
+    // nothing stays mapped then.  An allocation is opened once per process however often it is published.
+    int publish(void* ptr, size_t bytes, std::vector<void*>* mapped, std::vector<void*>* opened, bool* ok);
+    void release(std::vector<void*>* opened);
     // Address of (slot, offset) of world rank `r` in THIS process' address space.
     void* peer_ptr(int r, int slot, size_t offset) const;
 
@@ -90,7 +102,7 @@ private:
     void free_syncs();
 
     Comm world_;
-    bool inited_ = false, available_ = false;
+    bool inited_ = false, available_ = false, shared_device_ = false;
     const char* why_ = "not initialised";
     std::vector<Slot> slots_;
     uint64_t* flags_ = nullptr;  // [kChannels][world] + error word

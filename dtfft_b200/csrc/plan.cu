@@ -119,7 +119,16 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     // ---- backend choice (src/dtfft_config.F90:766-786; transpose_plan.F90:222) ----
     rc = peers_.init(comm_);
     if (rc) return rc;
-    int wanted = cfg_.backend == BACKEND_NONE ? BACKEND_NCCL : cfg_.backend;
+    // No backend named by the caller: the reference takes NCCL on CUDA (src/dtfft_config.F90:766-786).  Here the
+    // direct-store backend is the default whenever every rank can reach every other rank's memory (one NVSwitch
+    // box) and fused backends are enabled -- it takes any device pointer (handle.h: peer_bases) and falls back to
+    // NCCL per call for memory cudaIpc cannot share.  DTFFTB_DEFAULT_BACKEND=nccl keeps the reference's choice.
+    int wanted = cfg_.backend;
+    if (wanted == BACKEND_NONE) {
+        const char* e = getenv("DTFFTB_DEFAULT_BACKEND");
+        const bool keep_nccl = e && (e[0] == 'n' || e[0] == 'N') && (e[1] == 'c' || e[1] == 'C');
+        wanted = (P > 1 && peers_.available() && cfg_.enable_fused_backends && !keep_nccl) ? BACKEND_NVLINK_FUSED : BACKEND_NCCL;
+    }
     if (wanted != BACKEND_NCCL && wanted != BACKEND_NCCL_PIPELINED && wanted != BACKEND_NVLINK_FUSED)
         return DTFFT_ERROR_INVALID_BACKEND;
     if (wanted == BACKEND_NVLINK_FUSED && !peers_.available()) {
@@ -127,7 +136,10 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
         wanted = BACKEND_NCCL;
     }
     backend_ = P == 1 ? BACKEND_NONE : wanted;
-    if (P > 1) {
+    // test mode (several ranks time-slicing ONE device, fused backend only): NCCL refuses duplicate devices
+    const bool shared_device = peers_.shared_device();
+    if (shared_device && wanted != BACKEND_NVLINK_FUSED) return DTFFT_ERROR_GPU_NOT_SET;
+    if (P > 1 && !shared_device) {
         rc = init_nccl();
         if (rc) return rc;
     }
@@ -1146,7 +1158,52 @@ int Plan::run_transpose(int ttype, void* in, void* out, void* aux) {
     stat_launches_ += h.kernel_launches();
     stat_local_ += h.local_elements() * base_storage_;
     stat_remote_ += h.remote_elements() * base_storage_;
-    return h.execute(in, out, stream_, aux);
+    const int rc = h.execute(in, out, stream_, aux);
+    if (rc == DTFFTB_ERROR_NOT_REGISTERED && h.backend() == BACKEND_NVLINK_FUSED) return fallback_execute(false, ttype, in, out, aux);
+    return rc;
+}
+
+// A destination that cudaIpc cannot share (agreed on by every rank inside publish): this call -- and every
+// later one with such a buffer -- runs on the NCCL backend instead.  Logged once; CUDA-graph replay is
+// switched off for the plan because NCCL calls are kept out of graphs.
+int Plan::fallback_execute(bool reshape, int type, void* in, void* out, void* aux) {
+    auto& fb = reshape ? fb_rhandles_ : fb_handles_;
+    if (fb.empty()) {
+        if (!nccl_) return DTFFTB_ERROR_NOT_REGISTERED;
+        HandleContext ctx;
+        ctx.nccl = nccl_;
+        ctx.peers = &peers_;
+        ctx.effort = effort_;
+        ctx.no_shortcuts = true;  // the three-step schedule needs no workspace
+        std::vector<int> types;
+        if (reshape)
+            for (int t = R_X_BRICKS_TO_PENCILS; t <= R_Z_BRICKS_TO_PENCILS; ++t) types.push_back(t);
+        else
+            types = transpose_types();
+        for (int t : types) {
+            HandleSpec hs;
+            int rc = handle_spec(t, &hs);
+            if (rc) return rc;
+            std::unique_ptr<ReshapeHandle> h(new ReshapeHandle);
+            const int b = hs.members.size() > 1 ? BACKEND_NCCL : BACKEND_NONE;
+            rc = h->create(ctx, reshape ? 0 : t, reshape ? t : 0, hs.comm_id, hs.members, hs.me, hs.send, hs.recv, hs.es, b);
+            if (rc) return rc;
+            fb[t] = std::move(h);
+        }
+        log("NVLINK_FUSED: a buffer cannot be shared through cudaIpc; such calls use the NCCL backend");
+        if (graphs_enabled_) {
+            graphs_enabled_ = false;
+            if (!graphs_.empty()) {
+                cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(stream_, &st);
+                if (st == cudaStreamCaptureStatusNone) drop_graphs();
+            }
+        }
+    }
+    auto it = fb.find(type);
+    if (it == fb.end()) return DTFFTB_ERROR_INTERNAL;
+    ++stat_fallbacks_;
+    return it->second->execute(in, out, stream_, aux);
 }
 
 int Plan::run_reshape(int rtype, void* in, void* out, void* aux) {
@@ -1160,7 +1217,9 @@ int Plan::run_reshape(int rtype, void* in, void* out, void* aux) {
     stat_launches_ += h.kernel_launches();
     stat_local_ += h.local_elements() * es;
     stat_remote_ += h.remote_elements() * es;
-    return h.execute(in, out, stream_, aux);
+    const int rc = h.execute(in, out, stream_, aux);
+    if (rc == DTFFTB_ERROR_NOT_REGISTERED && h.backend() == BACKEND_NVLINK_FUSED) return fallback_execute(true, rtype, in, out, aux);
+    return rc;
 }
 
 int Plan::run_fft(int dim, void* a, void* b, int sign) {
@@ -1211,6 +1270,11 @@ int Plan::run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void
     }
     const int ctas = overlap_ctas_ > 0 ? overlap_ctas_ : sms;
     int rc = h.fused_begin(c, stream_);
+    if (rc == DTFFTB_ERROR_NOT_REGISTERED) {  // unshareable destination: sequential, NCCL stand-in
+        rc = run_fft(dim, a, b, sign);
+        if (rc) return rc;
+        return run_transpose(ttype, b, c, aux);
+    }
     if (rc) return rc;
     for (long long k = 0; k < nch; ++k) {
         const long long lo = slow * k / nch, hi = slow * (k + 1) / nch;
@@ -1314,6 +1378,11 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
     TraceRange trace(mode == 1 ? "Transpose pair (local || exchange)" : "Transpose pair (exchange || local)", kColorTranspose);
     if (mode == 1) {
         rc = h2.fused_begin(c, stream_);  // every member's `c` is free
+        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
+            rc = run_transpose(t1, a, b, aux);
+            if (rc) return rc;
+            return run_transpose(t2, b, c, aux);
+        }
         if (rc) return rc;
         for (long long k = 0; k < nch; ++k) {
             rc = h1.local_produce(a, b, (int)k, (int)nch, stream_);
@@ -1334,6 +1403,11 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
         stat_launches_ += 2 + 2 * nch;
     } else {
         rc = h1.fused_begin(b, stream_);  // every member's `b` is free
+        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
+            rc = run_transpose(t1, a, b, aux);
+            if (rc) return rc;
+            return run_transpose(t2, b, c, aux);
+        }
         if (rc) return rc;
         ce = cudaEventRecord(pair_start_, stream_);
         if (ce != cudaSuccess) return cuda_error(ce);
@@ -1452,10 +1526,23 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     // Second call: captured while it is enqueued.  Later calls: one cudaGraphLaunch.
     GraphKey key{in, out, a1, fwd};
     auto it = graphs_.find(key);
+    // peers hold mappings of my buffers (NVLINK_FUSED): an address that was freed and re-allocated since the
+    // graph was captured must go through the eager path again, which re-publishes it (handle.h: peer_bases)
+    unsigned long long ids[3] = {0, 0, 0};
+    if (comm_.size() > 1) {
+        ids[0] = buffer_id(in), ids[1] = buffer_id(out), ids[2] = buffer_id(a1);
+        if (it != graphs_.end() && (it->second.ids[0] != ids[0] || it->second.ids[1] != ids[1] || it->second.ids[2] != ids[2])) {
+            if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+            graphs_.erase(it);
+            it = graphs_.end();
+        }
+    }
     if (it == graphs_.end()) {
         if (graphs_.size() >= 16) drop_graphs();
         it = graphs_.emplace(key, GraphEntry{}).first;
+        for (int i = 0; i < 3; ++i) it->second.ids[i] = ids[i];
         rc = execute_schedule(in, out, fwd, a1, a2, inplace);
+        if (!graphs_enabled_) return rc;  // the call fell back to NCCL and dropped the graphs: `it` is gone
         // A schedule with overlapped stages stays eager: measured on 2 B200 (profiles/r01f_configs_auto_n2.jsonl
         // vs r01d_configs_n2.jsonl, 16384^2 slab) the two-stream pipeline loses its overlap when replayed as
         // graph branches (9.41 ms vs 8.55 ms eager), and such schedules are long enough not to be launch-bound.

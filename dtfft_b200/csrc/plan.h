@@ -101,6 +101,7 @@ public:
         drop_graphs();
     }
     int64_t graph_replays() const { return stat_graph_replays_; }
+    int64_t fallbacks() const { return stat_fallbacks_; }
     int overlap_chunks() const { return overlap_chunks_; }
     int64_t overlapped_stages() const { return stat_overlapped_; }
 
@@ -207,6 +208,12 @@ private:
     PeerRegistry peers_;
     std::map<int, std::unique_ptr<ReshapeHandle>> handles_;   // keyed by dtfft_transpose_t
     std::map<int, std::unique_ptr<ReshapeHandle>> rhandles_;  // keyed by dtfft_reshape_t
+    // NCCL stand-ins of the NVLINK_FUSED handles, built on first need: a caller's buffer that cudaIpc cannot
+    // export (stream-ordered or virtual-memory allocations) still has to work, like every device pointer
+    // does in the reference (src/dtfft_plan.F90:1769-1795).  Every rank falls back together (publish agrees).
+    std::map<int, std::unique_ptr<ReshapeHandle>> fb_handles_, fb_rhandles_;
+    int fallback_execute(bool reshape, int type, void* in, void* out, void* aux);
+    int64_t stat_fallbacks_ = 0;
     std::unique_ptr<FftExecutor> fft_[3];
     int fft_mapping_[3] = {0, 1, 2};
 
@@ -234,6 +241,7 @@ private:
         bool failed = false;
         int64_t launches = 0, local = 0, remote = 0, overlapped = 0;
         long long evictions = 0;  // handle_evictions() when the graph was captured
+        unsigned long long ids[3] = {0, 0, 0};  // buffer_id of (in, out, aux) at capture: a re-allocation voids the graph
     };
     long long handle_evictions() const;
     std::map<GraphKey, GraphEntry> graphs_;

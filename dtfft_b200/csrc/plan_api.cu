@@ -397,6 +397,7 @@ const char* dtfft_get_error_string(dtfft_error_t e) {
         case DTFFT_ERROR_INVALID_PLATFORM_BACKEND: return "backend not available on this platform";
         case DTFFTB_ERROR_NOT_REGISTERED: return "NVLINK_FUSED: `out` must be a registered (dtfft_mem_alloc) buffer";
         case DTFFTB_ERROR_COMM: return "host allgather callback failed";
+        case DTFFTB_ERROR_PEER_TIMEOUT: return "NVLINK_FUSED: a group member missed a device barrier (DTFFTB_PEER_TIMEOUT_MS); the plan is dead";
         case DTFFTB_ERROR_INTERNAL: return "internal error";
         default:
             if ((int)e <= DTFFTB_ERROR_NCCL_BASE && (int)e > DTFFTB_ERROR_INTERNAL) return "NCCL error";
@@ -535,6 +536,12 @@ dtfft_error_t dtfftb_plan_get_graph_replays(dtfft_plan_t plan, int64_t* n_replay
     PLAN_OR_RETURN(plan);
     if (!n_replays) return DTFFT_ERROR_INVALID_USAGE;
     *n_replays = P(plan)->graph_replays();
+    return DTFFT_SUCCESS;
+}
+dtfft_error_t dtfftb_plan_get_fallbacks(dtfft_plan_t plan, int64_t* n_fallbacks) {
+    PLAN_OR_RETURN(plan);
+    if (!n_fallbacks) return DTFFT_ERROR_INVALID_USAGE;
+    *n_fallbacks = P(plan)->fallbacks();
     return DTFFT_SUCCESS;
 }
 dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages) {

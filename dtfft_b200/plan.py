@@ -557,6 +557,13 @@ class Plan:
         _check(_lib.lib().dtfftb_plan_set_graphs(self._h, int(bool(enable))), "dtfftb_plan_set_graphs")
 
     @property
+    def fallbacks(self) -> int:
+        """NVLINK_FUSED: transpositions / reshapes that ran on the NCCL stand-in (buffer not shareable over cudaIpc)."""
+        n = C.c_int64(0)
+        _check(_lib.lib().dtfftb_plan_get_fallbacks(self._h, C.byref(n)), "dtfftb_plan_get_fallbacks")
+        return n.value
+
+    @property
     def graph_replays(self) -> int:
         n = C.c_int64(0)
         _check(_lib.lib().dtfftb_plan_get_graph_replays(self._h, C.byref(n)), "dtfftb_plan_get_graph_replays")

@@ -360,6 +360,9 @@ dtfft_error_t dtfftb_plan_get_overlap(dtfft_plan_t plan, int* nchunks);
  * unregistering a buffer drops the graphs. */
 dtfft_error_t dtfftb_plan_set_graphs(dtfft_plan_t plan, int enable);
 dtfft_error_t dtfftb_plan_get_graph_replays(dtfft_plan_t plan, int64_t* n_replays);
+/* NVLINK_FUSED: how many transpositions / reshapes of this plan ran on the NCCL stand-in because a caller's
+ * buffer could not be shared through cudaIpc (stream-ordered or virtual-memory allocations). */
+dtfft_error_t dtfftb_plan_get_fallbacks(dtfft_plan_t plan, int64_t* n_fallbacks);
 /* Number of FFT+transposition stages of the last dtfft_execute that ran overlapped. */
 dtfft_error_t dtfftb_plan_get_overlapped_stages(dtfft_plan_t plan, int64_t* n_stages);
 

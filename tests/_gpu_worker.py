@@ -23,10 +23,25 @@ def main():
     from oracle import pipeline as P
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # DTFFTB_ALLOW_SHARED_DEVICE=1 (tests/test_zz_shared_device_gpu.py): every rank on cuda:0, time-slicing the
+    # one GPU of the driver's box; NCCL refuses that, so the metadata plumbing is gloo and only the
+    # NVLINK_FUSED backend (cudaIpc + device barriers, both fine on one device) is exercised
+    shared = os.environ.get("DTFFTB_ALLOW_SHARED_DEVICE", "0") == "1"
+    if shared:
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     comm = TorchComm()
+
+    def allreduce_sum(np_vec):
+        tt = torch.from_numpy(np.asarray(np_vec, dtype=np.float64))
+        if not shared:
+            tt = tt.cuda()
+        dist.all_reduce(tt)
+        return tt.cpu().numpy()
     lay = [Layout.X_PENCILS, Layout.Y_PENCILS, Layout.Z_PENCILS]
 
     def oracle_pencil(p):
@@ -48,7 +63,7 @@ def main():
     def host(t, dtype, n):
         return t.cpu().numpy().view(dtype)[:n]
 
-    backends = [Backend.NCCL, Backend.NCCL_PIPELINED, Backend.NVLINK_FUSED]
+    backends = [Backend.NVLINK_FUSED] if shared else [Backend.NCCL, Backend.NCCL_PIPELINED, Backend.NVLINK_FUSED]
     if os.environ.get("DTFFTB_TEST_BACKENDS"):  # e.g. "NVLINK_FUSED": shorter runs on large boxes
         backends = [Backend[x] for x in os.environ["DTFFTB_TEST_BACKENDS"].split(",")]
     checked = 0
@@ -112,10 +127,8 @@ def main():
                 plan.execute(at, bt, Execute.FORWARD)
                 sync(plan)
                 got = host(bt, cdt, want.size).astype(np.complex128)
-                num = np.array([np.linalg.norm(got - want) ** 2, np.linalg.norm(want) ** 2])
-                tt = torch.from_numpy(num).cuda()
-                dist.all_reduce(tt)
-                rel = float(torch.sqrt(tt[0] / tt[1]))
+                tt = allreduce_sum([np.linalg.norm(got - want) ** 2, np.linalg.norm(want) ** 2])
+                rel = float(np.sqrt(tt[0] / tt[1]))
                 assert rel <= tol, (backend.name, cls.__name__, rel)
                 # the third call with the same buffers replays the CUDA graph captured during the second
                 if backend == Backend.NVLINK_FUSED:
@@ -247,6 +260,79 @@ def main():
             plan.mem_free(b_)
         plan.destroy()
         checked += 1
+
+    # Drop-in contract (src/dtfft_plan.F90:1769-1795: ANY device pointer is accepted): no backend named, no
+    # dtfft_mem_alloc -- plain torch allocations (cudaMalloc segments) through dtfft_transpose / dtfft_execute.
+    # The default backend on a peer-reachable box is NVLINK_FUSED; the buffers are published on first use.
+    if "DTFFTB_DEFAULT_BACKEND" not in os.environ and "DTFFT_BACKEND" not in os.environ:
+        dims = [72, 40, 56]
+        plan = PlanC2C(dims, comm=comm, config=Config(enable_z_slab=False))
+        assert plan.backend == Backend.NVLINK_FUSED, plan.backend
+        G = P.global_array(dims, np.complex128, kind="random")
+        pencils = [oracle_pencil(plan.get_pencil(lay[d])) for d in range(3)]
+        x, ywant, zwant = (P.pencil_slice(G, pencils[d]) for d in range(3))
+        nb = plan.alloc_bytes
+        for round_ in range(3):  # round 1, 2: freshly allocated tensors, quite possibly at the addresses of round 0
+            at = torch.full((nb,), 0xAB, dtype=torch.uint8, device="cuda")
+            bt = torch.full((nb,), 0xAB, dtype=torch.uint8, device="cuda")
+            ct = torch.full((nb,), 0xAB, dtype=torch.uint8, device="cuda")
+            at[: x.nbytes] = torch.from_numpy(x.view(np.uint8).copy()).cuda()
+            torch.cuda.synchronize()
+            dist.barrier()
+            plan.transpose(at, bt, 1)  # X -> Y into a plain buffer
+            sync(plan)
+            assert np.array_equal(host(bt, np.complex128, ywant.size).view(np.uint8), ywant.view(np.uint8)), ("drop-in X->Y", rank)
+            for rep in range(3):  # eager, captured, replayed
+                bt.fill_(0xAB)
+                ct.fill_(0xAB)
+                torch.cuda.synchronize()
+                dist.barrier()
+                plan.execute(at, bt, Execute.FORWARD)
+                sync(plan)
+                assert np.array_equal(host(bt, np.complex128, zwant.size).view(np.uint8), zwant.view(np.uint8)), ("drop-in fwd", rank, rep)
+                plan.execute(bt, ct, Execute.BACKWARD)
+                sync(plan)
+                assert np.array_equal(host(ct, np.complex128, x.size).view(np.uint8), x.view(np.uint8)), ("drop-in bwd", rank, rep)
+            assert plan.fallbacks == 0 and plan.peer_error() == 0
+            del at, bt, ct
+            torch.cuda.synchronize()
+            dist.barrier()
+            if round_ == 1:
+                torch.cuda.empty_cache()  # really returns the segments: the next round maps new allocations
+        # memory cudaIpc cannot export (stream-ordered allocations): the call must still work -- on the NCCL stand-in
+        import ctypes
+
+        if shared:  # no NCCL among ranks of one device
+            plan.destroy()
+            checked += 1
+        else:
+            rt = ctypes.CDLL("libcudart.so.12")
+            ptrs = []
+            for _ in range(3):
+                pv = ctypes.c_void_p(0)
+                assert rt.cudaMallocAsync(ctypes.byref(pv), ctypes.c_size_t(nb), ctypes.c_void_p(0)) == 0
+                ptrs.append(pv.value)
+            assert rt.cudaDeviceSynchronize() == 0
+            rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+            xb = np.ascontiguousarray(x).view(np.uint8)
+            assert rt.cudaMemcpy(ptrs[0], xb.ctypes.data, xb.nbytes, 1) == 0
+            dist.barrier()
+            plan.execute(ptrs[0], ptrs[1], Execute.FORWARD)
+            plan.execute(ptrs[1], ptrs[2], Execute.BACKWARD)
+            sync(plan)
+            back = np.empty_like(xb)
+            assert rt.cudaMemcpy(back.ctypes.data, ptrs[2], xb.nbytes, 2) == 0
+            assert np.array_equal(back, xb), ("fallback round trip", rank)
+            zb = np.empty(zwant.nbytes, np.uint8)
+            assert rt.cudaMemcpy(zb.ctypes.data, ptrs[1], zb.nbytes, 2) == 0
+            assert np.array_equal(zb, zwant.view(np.uint8)), ("fallback fwd", rank)
+            assert plan.fallbacks > 0, "stream-ordered memory should have taken the NCCL stand-in"
+            dist.barrier()
+            plan.destroy()
+            for pv in ptrs:
+                rt.cudaFreeAsync(ctypes.c_void_p(pv), ctypes.c_void_p(0))
+            rt.cudaDeviceSynchronize()
+            checked += 1
 
     # DTFFT_PATIENT: timed backend choice (run_autotune_backend), then a correct transposition
     plan = PlanC2C([128, 64, 96], comm=comm, effort=Effort.PATIENT, config=Config(enable_z_slab=False))
