@@ -29,64 +29,37 @@ template <> struct ElemT<4> { using type = unsigned int; };
 template <> struct ElemT<8> { using type = uint2; };
 template <> struct ElemT<16> { using type = uint4; };
 
-// Optional cache-policy variants of the global accesses (env DTFFTB_CACHE_HINT, default 0):
-//   0  plain ld.global / st.global (what every measured number in profiles/ uses)
-//   1  ld.global.nc.L1::no_allocate + st.global.L1::no_allocate (data is touched exactly once)
-//   2  plain loads + st.global.cs (evict-first streaming stores)
-// HINT is a template parameter, so the default instantiations contain no trace of the variants.
-template <int HINT, typename T>
-__device__ __forceinline__ T ld_payload(const T* p) {
-    if constexpr (HINT == 1 && sizeof(T) == 16) {
+// Payload accesses name the global state space explicitly: block bases come out of the descriptor table
+// (local or peer-mapped HBM), which would otherwise make them generic-space LD / ST in SASS.
+template <typename T>
+__device__ __forceinline__ T ld_global(const T* p) {
+    if constexpr (sizeof(T) == 16) {
         uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
         return *reinterpret_cast<T*>(&v);
-    } else if constexpr (HINT == 1 && sizeof(T) == 8) {
+    } else if constexpr (sizeof(T) == 8) {
         uint2 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
         return *reinterpret_cast<T*>(&v);
-    } else if constexpr (HINT == 1 && sizeof(T) == 4) {
+    } else {
         unsigned v;
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
         return *reinterpret_cast<T*>(&v);
-    } else {
-        return *p;
     }
 }
 
-template <int HINT, typename T>
-__device__ __forceinline__ void st_payload(T* p, const T& val) {
-    if constexpr (HINT == 1 && sizeof(T) == 16) {
+template <typename T>
+__device__ __forceinline__ void st_global(T* p, const T& val) {
+    if constexpr (sizeof(T) == 16) {
         const uint4 v = *reinterpret_cast<const uint4*>(&val);
-        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    } else if constexpr (HINT == 1 && sizeof(T) == 8) {
+        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    } else if constexpr (sizeof(T) == 8) {
         const uint2 v = *reinterpret_cast<const uint2*>(&val);
-        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
-    } else if constexpr (HINT == 1 && sizeof(T) == 4) {
-        const unsigned v = *reinterpret_cast<const unsigned*>(&val);
-        asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-    } else if constexpr (HINT == 2 && sizeof(T) == 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&val);
-        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    } else if constexpr (HINT == 2 && sizeof(T) == 8) {
-        const uint2 v = *reinterpret_cast<const uint2*>(&val);
-        asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
-    } else if constexpr (HINT == 2 && sizeof(T) == 4) {
-        const unsigned v = *reinterpret_cast<const unsigned*>(&val);
-        asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
     } else {
-        *p = val;
+        const unsigned v = *reinterpret_cast<const unsigned*>(&val);
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
     }
-}
-
-int cache_hint_from_env() {
-    static int hint = -1;
-    if (hint < 0) {
-        const char* e = getenv("DTFFTB_CACHE_HINT");
-        hint = e ? atoi(e) : 0;
-        if (hint < 0 || hint > 2) hint = 0;
-    }
-    return hint;
 }
 
 __device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
@@ -203,7 +176,7 @@ __device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks,
 // ---------------------------------------------------------------------------------
 // Family T
 // ---------------------------------------------------------------------------------
-template <typename T, int KA, int KB, int ROWS, int HINT, bool SYNC = false>
+template <typename T, int KA, int KB, int ROWS, bool SYNC = false>
 __global__ void __launch_bounds__(32 * ROWS)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
                            int nblocks, long long total_items, const FusedSync* __restrict__ sync = nullptr) {
@@ -240,11 +213,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int a = a0 + tx + 32 * k;
-                if constexpr (HINT == 0) {
-                    if (a < n0 && b < n1) regs[j][k] = src[a + (long long)b * is1];
-                } else {
-                    if (a < n0 && b < n1) regs[j][k] = ld_payload<HINT>(src + a + (long long)b * is1);
-                }
+                if (a < n0 && b < n1) regs[j][k] = ld_global(src + a + (long long)b * is1);
             }
         }
 #pragma unroll
@@ -258,11 +227,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int b = b0 + tx + 32 * k;
-                if constexpr (HINT == 0) {
-                    if (a < n0 && b < n1) dst[(long long)a * os0 + b] = tile[(j * ROWS + ty) * PITCH + tx + 32 * k];
-                } else {
-                    if (a < n0 && b < n1) st_payload<HINT>(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k]);
-                }
+                if (a < n0 && b < n1) st_global(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k]);
             }
         }
         __syncthreads();
@@ -270,12 +235,12 @@ __global__ void __launch_bounds__(32 * ROWS)
     if constexpr (SYNC) fused_sync_leave(sync);
 }
 
-template <int ES, int KA, int KB, int ROWS, int HINT, bool SYNC = false>
-cudaError_t launch_T_hint(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
+template <int ES, int KA, int KB, int ROWS, bool SYNC = false>
+cudaError_t launch_T_sync(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
                           cudaStream_t stream, const FusedSync* sync = nullptr) {
     using T = typename ElemT<ES>::type;
     constexpr size_t smem = (size_t)(32 * KA) * (32 * KB + 1) * ES;
-    auto kern = transpose_tiles_kernel<T, KA, KB, ROWS, HINT, SYNC>;
+    auto kern = transpose_tiles_kernel<T, KA, KB, ROWS, SYNC>;
     if (smem > 48 * 1024) {
         // function attributes are per device: one flag per (instantiation, device)
         static bool attr_set[kMaxDevices] = {};
@@ -300,13 +265,8 @@ cudaError_t launch_T_hint(const void* in, void* out, const BlockDesc* blocks, in
 template <int ES, int KA, int KB, int ROWS>
 cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
                      cudaStream_t stream, const FusedSync* sync) {
-    // the in-kernel barriers come with the default (measured) access policy only
-    if (sync) return launch_T_hint<ES, KA, KB, ROWS, 0, true>(in, out, blocks, nblocks, total, grid_cap, stream, sync);
-    switch (cache_hint_from_env()) {
-        case 1: return launch_T_hint<ES, KA, KB, ROWS, 1>(in, out, blocks, nblocks, total, grid_cap, stream);
-        case 2: return launch_T_hint<ES, KA, KB, ROWS, 2>(in, out, blocks, nblocks, total, grid_cap, stream);
-        default: return launch_T_hint<ES, KA, KB, ROWS, 0>(in, out, blocks, nblocks, total, grid_cap, stream);
-    }
+    if (sync) return launch_T_sync<ES, KA, KB, ROWS, true>(in, out, blocks, nblocks, total, grid_cap, stream, sync);
+    return launch_T_sync<ES, KA, KB, ROWS, false>(in, out, blocks, nblocks, total, grid_cap, stream);
 }
 
 template <int ES>
@@ -330,7 +290,7 @@ cudaError_t dispatch_T(TileCfg c, const void* in, void* out, const BlockDesc* b,
 // ---------------------------------------------------------------------------------
 // Family R
 // ---------------------------------------------------------------------------------
-template <typename V, int TX, int HINT, bool SYNC = false>
+template <typename V, int TX, bool SYNC = false>
 __global__ void __launch_bounds__(kRowsThreads)
     rows_copy_kernel(const V* __restrict__ in, V* __restrict__ out, const BlockDesc* __restrict__ blocks, int nblocks,
                      long long total_items, const FusedSync* __restrict__ sync = nullptr) {
@@ -360,20 +320,12 @@ __global__ void __launch_bounds__(kRowsThreads)
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                if constexpr (HINT == 0) {
-                    if (row < n1) regs[r] = src[col + (long long)row * is1];
-                } else {
-                    if (row < n1) regs[r] = ld_payload<HINT>(src + col + (long long)row * is1);
-                }
+                if (row < n1) regs[r] = ld_global(src + col + (long long)row * is1);
             }
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                if constexpr (HINT == 0) {
-                    if (row < n1) dst[col + (long long)row * os1] = regs[r];
-                } else {
-                    if (row < n1) st_payload<HINT>(dst + col + (long long)row * os1, regs[r]);
-                }
+                if (row < n1) st_global(dst + col + (long long)row * os1, regs[r]);
             }
         }
     }
@@ -387,15 +339,10 @@ cudaError_t launch_R(const void* in, void* out, const BlockDesc* blocks, int nbl
     long long g = total < grid_cap ? total : grid_cap;
     const V* pin = reinterpret_cast<const V*>(in);
     V* pout = reinterpret_cast<V*>(out);
-    if (sync) {  // in-kernel barriers: default access policy only
-        rows_copy_kernel<V, TX, 0, true><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total, sync);
-        return cudaGetLastError();
-    }
-    switch (cache_hint_from_env()) {
-        case 1: rows_copy_kernel<V, TX, 1><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total); break;
-        case 2: rows_copy_kernel<V, TX, 2><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total); break;
-        default: rows_copy_kernel<V, TX, 0><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total); break;
-    }
+    if (sync)
+        rows_copy_kernel<V, TX, true><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total, sync);
+    else
+        rows_copy_kernel<V, TX, false><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total);
     return cudaGetLastError();
 }
 

@@ -32,7 +32,6 @@ def time_ms(fn, warmup=3, iters=10):
 def quick(args):
     n = args.n
     N = n ** 3
-    hint = os.environ.get("DTFFTB_CACHE_HINT", "0")
     for es in (16, 8, 4):
         a = torch.empty(N * es, dtype=torch.uint8, device="cuda")
         a.random_(0, 255)
@@ -42,7 +41,7 @@ def quick(args):
                          (KERNEL_PERMUTE_BACKWARD_START, "backward_start")):
             k = Kernel().create([n, n, n], 0, es, kt)
             ms = time_ms(lambda: k.execute(a, b), warmup=5, iters=20)
-            print(json.dumps({"what": name, "es": es, "n": n, "cache_hint": hint, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
+            print(json.dumps({"what": name, "es": es, "n": n, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
             k.destroy()
         P = 8
         nxx = n // P
@@ -52,7 +51,7 @@ def quick(args):
         for kt, name in ((KERNEL_UNPACK, "unpack8"), (KERNEL_PERMUTE_BACKWARD_END, "backward_end8")):
             k = Kernel().create([n, n, n], 0, es, kt, nd)
             ms = time_ms(lambda: k.execute(a, b), warmup=5, iters=20)
-            print(json.dumps({"what": name, "es": es, "n": n, "cache_hint": hint, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
+            print(json.dumps({"what": name, "es": es, "n": n, "ms": ms, "gbs": gb / ms * 1e3}), flush=True)
             k.destroy()
         del a, b
         torch.cuda.empty_cache()
@@ -63,7 +62,7 @@ def main():
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--out", default="gpurun_out/kbench.jsonl")
     ap.add_argument("--quick", action="store_true",
-                    help="default tile / grid of every kernel only (A/B of process-wide switches such as DTFFTB_CACHE_HINT)")
+                    help="default tile / grid of every kernel only (A/B of process-wide switches such as DTFFTB_TILE)")
     args = ap.parse_args()
     if args.quick:
         return quick(args)
