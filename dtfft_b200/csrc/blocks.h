@@ -54,25 +54,4 @@ struct BlockDesc {
     FastDiv div0, div1;   // fast division by tiles0 / tiles1
 };
 
-// Opt-in (DTFFTB_FUSED_SYNC=1): the two device barriers that bracket the fused NVLink kernel
-// ("every member's destination is free" / "every block has landed", peer.h) folded INTO the kernel.
-// The first CTA to arrive announces "my destination is free" to every member; every CTA waits for
-// all members' announcements before its first store; the last CTA to finish (ticket counter, after
-// a system-scope fence by every CTA) announces "my blocks have landed" and waits for everybody's.
-// Lives in device memory; epochs are the same counters the stand-alone barrier kernel advances,
-// so both forms can be mixed on one communicator and replayed from CUDA graphs.
-struct FusedSync {
-    unsigned long long* const* peer_flags;  // [n] flags base of every member (peer-mapped; mine = local)
-    unsigned long long* my_flags;
-    const int* members;                     // [n] world ranks
-    int n, me;                              // group size, my WORLD rank
-    long long row_free, row_landed;         // flag rows (channel * world size)
-    unsigned long long* epoch_free;         // group epoch counters of the two channels
-    unsigned long long* epoch_landed;
-    unsigned int* tickets;                  // [0] CTAs that entered, [1] CTAs that finished
-    unsigned long long* err;                // sticky error word (time-out), device memory: read by the kernels
-    unsigned long long* err_host;           // its mirror in mapped host memory: read by the API without a sync
-    long long timeout_cycles;
-};
-
 }  // namespace dtfftb

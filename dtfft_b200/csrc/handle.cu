@@ -212,17 +212,6 @@ int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
     }
     // channel: one pair per 1-D communicator id
     const int ch_free = 2 * (comm_id_ - 1), ch_landed = ch_free + 1;
-    // DTFFTB_FUSED_SYNC=1 (opt-in until measured): both barriers run inside the fused kernel -- one
-    // launch instead of three.  A rank with nothing to store has no kernel to fold them into and
-    // uses the stand-alone barriers; both forms advance the same epochs, so they pair up.
-    static const bool fold = [] {
-        const char* e = getenv("DTFFTB_FUSED_SYNC");
-        return e && atoi(e) != 0;
-    }();
-    if (fold && !it->second->is_noop()) {
-        if (const FusedSync* sync = peers.fused_sync(members_, ch_free, ch_landed))
-            return it->second->execute_all(in, out, stream, sync);
-    }
     rc = peers.barrier(members_, ch_free, stream);  // every member's `out` is free
     if (rc) return rc;
     rc = it->second->execute_all(in, out, stream);

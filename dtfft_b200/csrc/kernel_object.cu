@@ -575,9 +575,8 @@ int Kernel::pick_unit(const void* in, const void* out) const {
     return u;
 }
 
-int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream,
-                   const FusedSync* sync) {
-    if (t.nblocks == 0 || t.total_items == 0) return sync ? DTFFTB_ERROR_INTERNAL : DTFFT_SUCCESS;
+int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream) {
+    if (t.nblocks == 0 || t.total_items == 0) return DTFFT_SUCCESS;
     cudaError_t ce;
     const int cap = grid_limit_ > 0 ? std::min(grid_cap_, grid_limit_) : grid_cap_;
     if (family_ == FAM_T) {
@@ -587,10 +586,10 @@ int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cu
         if ((reinterpret_cast<uintptr_t>(in) & mask) || (reinterpret_cast<uintptr_t>(out) & mask)) return DTFFT_ERROR_INVALID_USAGE;
         for (void* p : peer_out_)
             if (reinterpret_cast<uintptr_t>(p) & mask) return DTFFT_ERROR_INVALID_USAGE;
-        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream, sync);
+        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);
     } else {
         const int slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
-        ce = launch_rows(unit, tx_slot_[slot], in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream, sync);
+        ce = launch_rows(unit, tx_slot_[slot], in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);
     }
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
@@ -637,10 +636,9 @@ int Kernel::execute(const void* in, void* out, cudaStream_t stream, int neighbor
     return DTFFT_SUCCESS;
 }
 
-int Kernel::execute_all(const void* in, void* out, cudaStream_t stream, const FusedSync* sync) {
+int Kernel::execute_all(const void* in, void* out, cudaStream_t stream) {
     if (!created_) return DTFFTB_ERROR_INTERNAL;
     if (dry_) return DTFFT_ERROR_GPU_NOT_SET;
-    if (sync && (noop_ || family_ == FAM_COPY)) return DTFFTB_ERROR_INTERNAL;  // a folded barrier needs a real launch
     if (noop_) return DTFFT_SUCCESS;
     if (family_ == FAM_COPY) {
         if (type_ == K_COPY) return execute(in, out, stream, 0, false);
@@ -656,7 +654,7 @@ int Kernel::execute_all(const void* in, void* out, cudaStream_t stream, const Fu
         unit = pick_unit(in, out);
         slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
     }
-    return launch(all_[slot], unit, in, out, stream, sync);
+    return launch(all_[slot], unit, in, out, stream);
 }
 
 int Kernel::set_peer_out(void* const* out_bases, const int64_t* out_displs_override) {

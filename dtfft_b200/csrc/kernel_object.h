@@ -65,8 +65,7 @@ public:
     // global-index intersections rather than from neighbor_data.
     int create_boxes(Family family, int64_t base_storage, const std::vector<Box>& boxes);
     int execute(const void* in, void* out, cudaStream_t stream, int neighbor, bool sync);
-    // `sync` (device pointer, optional): fold the fused path's group barriers into the launch (blocks.h: FusedSync)
-    int execute_all(const void* in, void* out, cudaStream_t stream, const FusedSync* sync = nullptr);
+    int execute_all(const void* in, void* out, cudaStream_t stream);
     int set_peer_out(void* const* out_bases, const int64_t* out_displs_override);
     int set_tile(int ka, int kb, int rows);
     // Run as a persistent kernel of at most `max_ctas` CTAs (0 = no limit).  Used when the launch
@@ -107,8 +106,7 @@ public:
 
 private:
     int rebuild_tables();
-    int launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream,
-               const FusedSync* sync = nullptr);
+    int launch(const DeviceTable& t, int unit, const void* in, void* out, cudaStream_t stream);
     int pick_unit(const void* in, const void* out) const;
 
     bool created_ = false, noop_ = true, custom_ = false, dry_ = false;

@@ -94,72 +94,6 @@ __device__ __forceinline__ ItemPos decode_item(const BlockDesc& d, long long ite
     return p;
 }
 
-// ---------------------------------------------------------------------------------
-// In-kernel group barriers of the fused NVLink path (blocks.h: FusedSync), SYNC instantiations only
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ void sync_wait_flag(const unsigned long long* flag, unsigned long long epoch,
-                                               const FusedSync* s) {
-    const long long t0 = clock64();
-    unsigned long long v;
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        if (v >= epoch) break;
-        if (clock64() - t0 > s->timeout_cycles) {  // fatal: see peer_barrier_kernel
-            *reinterpret_cast<volatile unsigned long long*>(s->err) = 1;
-            *reinterpret_cast<volatile unsigned long long*>(s->err_host) = 1;
-            __threadfence_system();
-            break;
-        }
-        __nanosleep(64);
-    }
-}
-
-// Before the first store of a CTA: every member's destination must be free for this epoch.
-__device__ __forceinline__ void fused_sync_enter(const FusedSync* __restrict__ s) {
-    __shared__ unsigned s_first;
-    const int t = threadIdx.y * blockDim.x + threadIdx.x;
-    if (t == 0) s_first = atomicAdd(&s->tickets[0], 1u) == 0u ? 1u : 0u;
-    __syncthreads();
-    // the epoch counter is advanced by the LAST CTA to leave, i.e. after every CTA has read it here
-    const unsigned long long epoch = *reinterpret_cast<const volatile unsigned long long*>(s->epoch_free) + 1ull;
-    if (t < s->n) {
-        if (s_first) {  // earlier work on this stream is complete: my destination is free
-            unsigned long long* remote = s->peer_flags[t] + s->row_free + s->me;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
-        }
-        sync_wait_flag(s->my_flags + s->row_free + s->members[t], epoch, s);
-    }
-    __syncthreads();
-}
-
-// After the last store of a CTA: the last CTA of the grid tells every member that my blocks have
-// landed and waits until everybody's have, so the next kernel on the stream may read the destination.
-__device__ __forceinline__ void fused_sync_leave(const FusedSync* __restrict__ s) {
-    __shared__ unsigned s_last;
-    const int t = threadIdx.y * blockDim.x + threadIdx.x;
-    __syncthreads();
-    if (t == 0) {
-        __threadfence_system();  // this CTA's stores (ordered before by the barrier above) are visible system-wide
-        s_last = atomicAdd(&s->tickets[1], 1u) == gridDim.x - 1u ? 1u : 0u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence_system();  // pairs with the fences of the CTAs whose tickets were observed
-    const unsigned long long epoch = *reinterpret_cast<const volatile unsigned long long*>(s->epoch_landed) + 1ull;
-    if (t < s->n) {
-        unsigned long long* remote = s->peer_flags[t] + s->row_landed + s->me;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
-        sync_wait_flag(s->my_flags + s->row_landed + s->members[t], epoch, s);
-    }
-    __syncthreads();
-    if (t == 0) {  // ready for the next launch (ordered by the stream)
-        *s->epoch_free += 1ull;
-        *s->epoch_landed = epoch;
-        s->tickets[0] = 0u;
-        s->tickets[1] = 0u;
-    }
-}
-
 // Fused NVLink tables carry the address of the sticky peer-error word (blocks.h: BlockDesc::abort).  Once
 // a device barrier has timed out the destination was never announced free (or blocks never landed):
 // every later kernel of the group stores nothing, and the next API call returns
@@ -176,10 +110,10 @@ __device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks,
 // ---------------------------------------------------------------------------------
 // Family T
 // ---------------------------------------------------------------------------------
-template <typename T, int KA, int KB, int ROWS, bool SYNC = false>
+template <typename T, int KA, int KB, int ROWS>
 __global__ void __launch_bounds__(32 * ROWS)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
-                           int nblocks, long long total_items, const FusedSync* __restrict__ sync = nullptr) {
+                           int nblocks, long long total_items) {
     constexpr int TA = 32 * KA, TB = 32 * KB;
     constexpr int PITCH = TB + 1;
     constexpr int LD_ROWS = TB / ROWS;  // b-rows each thread loads
@@ -188,7 +122,6 @@ __global__ void __launch_bounds__(32 * ROWS)
     T* tile = reinterpret_cast<T*>(smem_raw);  // tile[a][b], pitch PITCH
 
     const int tx = threadIdx.x, ty = threadIdx.y;
-    if constexpr (SYNC) fused_sync_enter(sync);
     const bool aborted = peer_abort(blocks, ty * 32 + tx);
 
     // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
@@ -232,15 +165,14 @@ __global__ void __launch_bounds__(32 * ROWS)
         }
         __syncthreads();
     }
-    if constexpr (SYNC) fused_sync_leave(sync);
 }
 
-template <int ES, int KA, int KB, int ROWS, bool SYNC = false>
-cudaError_t launch_T_sync(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
-                          cudaStream_t stream, const FusedSync* sync = nullptr) {
+template <int ES, int KA, int KB, int ROWS>
+cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
+                     cudaStream_t stream) {
     using T = typename ElemT<ES>::type;
     constexpr size_t smem = (size_t)(32 * KA) * (32 * KB + 1) * ES;
-    auto kern = transpose_tiles_kernel<T, KA, KB, ROWS, SYNC>;
+    auto kern = transpose_tiles_kernel<T, KA, KB, ROWS>;
     if (smem > 48 * 1024) {
         // function attributes are per device: one flag per (instantiation, device)
         static bool attr_set[kMaxDevices] = {};
@@ -258,22 +190,15 @@ cudaError_t launch_T_sync(const void* in, void* out, const BlockDesc* blocks, in
     }
     long long g = total < grid_cap ? total : grid_cap;
     kern<<<(unsigned)g, dim3(32, ROWS), smem, stream>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out),
-                                                        blocks, nblocks, total, SYNC ? sync : nullptr);
+                                                        blocks, nblocks, total);
     return cudaGetLastError();
-}
-
-template <int ES, int KA, int KB, int ROWS>
-cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
-                     cudaStream_t stream, const FusedSync* sync) {
-    if (sync) return launch_T_sync<ES, KA, KB, ROWS, true>(in, out, blocks, nblocks, total, grid_cap, stream, sync);
-    return launch_T_sync<ES, KA, KB, ROWS, false>(in, out, blocks, nblocks, total, grid_cap, stream);
 }
 
 template <int ES>
 cudaError_t dispatch_T(TileCfg c, const void* in, void* out, const BlockDesc* b, int nb, long long total, int cap,
-                       cudaStream_t s, const FusedSync* sync) {
+                       cudaStream_t s) {
 #define DTFFTB_T_CASE(KA_, KB_, R_) \
-    if (c.ka == KA_ && c.kb == KB_ && c.rows == R_) return launch_T<ES, KA_, KB_, R_>(in, out, b, nb, total, cap, s, sync);
+    if (c.ka == KA_ && c.kb == KB_ && c.rows == R_) return launch_T<ES, KA_, KB_, R_>(in, out, b, nb, total, cap, s);
     DTFFTB_T_CASE(1, 1, 4)
     DTFFTB_T_CASE(1, 1, 8)
     DTFFTB_T_CASE(1, 1, 16)
@@ -290,14 +215,13 @@ cudaError_t dispatch_T(TileCfg c, const void* in, void* out, const BlockDesc* b,
 // ---------------------------------------------------------------------------------
 // Family R
 // ---------------------------------------------------------------------------------
-template <typename V, int TX, bool SYNC = false>
+template <typename V, int TX>
 __global__ void __launch_bounds__(kRowsThreads)
     rows_copy_kernel(const V* __restrict__ in, V* __restrict__ out, const BlockDesc* __restrict__ blocks, int nblocks,
-                     long long total_items, const FusedSync* __restrict__ sync = nullptr) {
+                     long long total_items) {
     constexpr int TY = kRowsThreads / TX;
     constexpr int UR = kRowsPerThread;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-    if constexpr (SYNC) fused_sync_enter(sync);
     const bool aborted = peer_abort(blocks, (int)threadIdx.x);
 
     // Fused NVLink tables interleave the peers: consecutive CTAs take items spread over the whole
@@ -329,33 +253,29 @@ __global__ void __launch_bounds__(kRowsThreads)
             }
         }
     }
-    if constexpr (SYNC) fused_sync_leave(sync);
 }
 
 template <int U, int TX>
 cudaError_t launch_R(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
-                     cudaStream_t stream, const FusedSync* sync) {
+                     cudaStream_t stream) {
     using V = typename ElemT<U>::type;
     long long g = total < grid_cap ? total : grid_cap;
     const V* pin = reinterpret_cast<const V*>(in);
     V* pout = reinterpret_cast<V*>(out);
-    if (sync)
-        rows_copy_kernel<V, TX, true><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total, sync);
-    else
-        rows_copy_kernel<V, TX, false><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total);
+    rows_copy_kernel<V, TX><<<(unsigned)g, kRowsThreads, 0, stream>>>(pin, pout, blocks, nblocks, total);
     return cudaGetLastError();
 }
 
 template <int U>
 cudaError_t dispatch_R(int tx, const void* in, void* out, const BlockDesc* b, int nb, long long total, int cap,
-                       cudaStream_t s, const FusedSync* sync) {
+                       cudaStream_t s) {
     switch (tx) {
-        case 8: return launch_R<U, 8>(in, out, b, nb, total, cap, s, sync);
-        case 16: return launch_R<U, 16>(in, out, b, nb, total, cap, s, sync);
-        case 32: return launch_R<U, 32>(in, out, b, nb, total, cap, s, sync);
-        case 64: return launch_R<U, 64>(in, out, b, nb, total, cap, s, sync);
-        case 128: return launch_R<U, 128>(in, out, b, nb, total, cap, s, sync);
-        case 256: return launch_R<U, 256>(in, out, b, nb, total, cap, s, sync);
+        case 8: return launch_R<U, 8>(in, out, b, nb, total, cap, s);
+        case 16: return launch_R<U, 16>(in, out, b, nb, total, cap, s);
+        case 32: return launch_R<U, 32>(in, out, b, nb, total, cap, s);
+        case 64: return launch_R<U, 64>(in, out, b, nb, total, cap, s);
+        case 128: return launch_R<U, 128>(in, out, b, nb, total, cap, s);
+        case 256: return launch_R<U, 256>(in, out, b, nb, total, cap, s);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -371,23 +291,23 @@ bool transpose_cfg_supported(int es, TileCfg c) {
 }
 
 cudaError_t launch_transpose(int es, TileCfg cfg, const void* in, void* out, const BlockDesc* d_blocks, int nblocks,
-                             long long total_items, int grid_cap, cudaStream_t stream, const FusedSync* sync) {
-    if (total_items <= 0) return sync ? cudaErrorInvalidValue : cudaSuccess;  // a barrier needs a launch
+                             long long total_items, int grid_cap, cudaStream_t stream) {
+    if (total_items <= 0) return cudaSuccess;
     switch (es) {
-        case 4: return dispatch_T<4>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
-        case 8: return dispatch_T<8>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
-        case 16: return dispatch_T<16>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
+        case 4: return dispatch_T<4>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
+        case 8: return dispatch_T<8>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
+        case 16: return dispatch_T<16>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t launch_rows(int unit, int tx, const void* in, void* out, const BlockDesc* d_blocks, int nblocks,
-                        long long total_items, int grid_cap, cudaStream_t stream, const FusedSync* sync) {
-    if (total_items <= 0) return sync ? cudaErrorInvalidValue : cudaSuccess;
+                        long long total_items, int grid_cap, cudaStream_t stream) {
+    if (total_items <= 0) return cudaSuccess;
     switch (unit) {
-        case 4: return dispatch_R<4>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
-        case 8: return dispatch_R<8>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
-        case 16: return dispatch_R<16>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream, sync);
+        case 4: return dispatch_R<4>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
+        case 8: return dispatch_R<8>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
+        case 16: return dispatch_R<16>(tx, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
         default: return cudaErrorInvalidValue;
     }
 }

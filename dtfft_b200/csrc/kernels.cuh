@@ -15,15 +15,13 @@ struct TileCfg {
 
 // Family T: out[b-contiguous] <- in[a-contiguous] for every block of the table.
 // `es` = element bytes (4, 8, 16).  Table lives in device memory.
-// `sync` (device pointer, may be null): fold the group barriers of the fused NVLink path into the launch.
 cudaError_t launch_transpose(int es, TileCfg cfg, const void* in, void* out, const BlockDesc* d_blocks,
-                             int nblocks, long long total_items, int grid_cap, cudaStream_t stream,
-                             const FusedSync* sync = nullptr);
+                             int nblocks, long long total_items, int grid_cap, cudaStream_t stream);
 
 // Family R: row copy in units of `unit` bytes (4, 8, 16); `tx` = threads along the row
 // (power of two, 8..256).  Descriptors are pre-scaled to units.
 cudaError_t launch_rows(int unit, int tx, const void* in, void* out, const BlockDesc* d_blocks, int nblocks,
-                        long long total_items, int grid_cap, cudaStream_t stream, const FusedSync* sync = nullptr);
+                        long long total_items, int grid_cap, cudaStream_t stream);
 
 // Rows each thread moves per tile in family R (tile = tx units x (256/tx)*kRowsPerThread rows).
 constexpr int kRowsPerThread = 8;

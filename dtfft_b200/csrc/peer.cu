@@ -389,52 +389,6 @@ PeerRegistry::Group* PeerRegistry::group_for(const std::vector<int>& members, in
     return &it->second;
 }
 
-const FusedSync* PeerRegistry::fused_sync(const std::vector<int>& members, int channel_free, int channel_landed) {
-    if (!available_ || !flags_) return nullptr;
-    const int n = (int)members.size();
-    if (n <= 1 || n > 128) return nullptr;
-    if (channel_free < 0 || channel_free >= kChannels || channel_landed < 0 || channel_landed >= kChannels) return nullptr;
-    auto key = std::make_pair(channel_free, members);
-    auto it = syncs_.find(key);
-    if (it != syncs_.end()) return it->second.d_state;
-    int rc = 0;
-    Group* gf = group_for(members, channel_free, &rc);
-    if (!gf) return nullptr;
-    Group* gl = group_for(members, channel_landed, &rc);
-    if (!gl) return nullptr;
-    const int P = world_.size();
-    SyncEntry e;
-    if (cudaMalloc(&e.d_state, sizeof(FusedSync)) != cudaSuccess || cudaMalloc(&e.d_tickets, 2 * sizeof(unsigned int)) != cudaSuccess) {
-        cudaGetLastError();
-        if (e.d_state) cudaFree(e.d_state);
-        return nullptr;
-    }
-    cudaMemset(e.d_tickets, 0, 2 * sizeof(unsigned int));
-    FusedSync h{};
-    h.peer_flags = reinterpret_cast<unsigned long long* const*>(gf->d_peer_flags);
-    h.my_flags = reinterpret_cast<unsigned long long*>(flags_);
-    h.members = gf->d_members;
-    h.n = n, h.me = world_.rank();
-    h.row_free = (long long)channel_free * P, h.row_landed = (long long)channel_landed * P;
-    h.epoch_free = reinterpret_cast<unsigned long long*>(gf->d_epoch);
-    h.epoch_landed = reinterpret_cast<unsigned long long*>(gl->d_epoch);
-    h.tickets = e.d_tickets;
-    h.err = reinterpret_cast<unsigned long long*>(flags_ + (size_t)kChannels * P);
-    h.err_host = reinterpret_cast<unsigned long long*>(d_err_host_);
-    h.timeout_cycles = timeout_cycles_;  // as barrier(): then a sticky, fatal error instead of a hung GPU
-    cudaMemcpy(e.d_state, &h, sizeof(h), cudaMemcpyHostToDevice);
-    syncs_.emplace(key, e);
-    return e.d_state;
-}
-
-void PeerRegistry::free_syncs() {
-    for (auto& kv : syncs_) {
-        if (kv.second.d_state) cudaFree(kv.second.d_state);
-        if (kv.second.d_tickets) cudaFree(kv.second.d_tickets);
-    }
-    syncs_.clear();
-}
-
 int PeerRegistry::barrier(const std::vector<int>& members, int channel, cudaStream_t stream) {
     if (!available_) return DTFFTB_ERROR_INTERNAL;
     const int n = (int)members.size();
@@ -459,7 +413,6 @@ int PeerRegistry::reset_barriers() {
     cudaError_t ce = cudaDeviceSynchronize();  // my barriers have completed ...
     if (ce != cudaSuccess) return cuda_error(ce);
     world_.barrier();                          // ... and so have everybody's: nobody reads or writes flags now
-    free_syncs();
     for (auto& kv : groups_) {
         if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
         if (kv.second.d_members) cudaFree(kv.second.d_members);
@@ -481,7 +434,6 @@ int PeerRegistry::error_state() const {
 
 void PeerRegistry::destroy() {
     if (!inited_) return;
-    free_syncs();
     for (auto& kv : groups_) {
         if (kv.second.d_peer_flags) cudaFree(kv.second.d_peer_flags);
         if (kv.second.d_members) cudaFree(kv.second.d_members);

@@ -58,10 +58,6 @@ public:
     // Enqueue a barrier among `members` (world ranks, must contain me) on `stream`.
     // `channel` separates independent groups (1-D communicator id 1..3, x2 phases).
     int barrier(const std::vector<int>& members, int channel, cudaStream_t stream);
-    // Device-resident state for folding the two barriers of a fused transposition into its kernel
-    // (blocks.h: FusedSync): channels `channel_free` / `channel_landed`, same epoch counters as
-    // barrier().  Returns nullptr when the group is too large for one CTA to poll (> 128 members).
-    const FusedSync* fused_sync(const std::vector<int>& members, int channel_free, int channel_landed);
     // Collective.  Forget every barrier group and zero the flags: must be called when the 1-D
     // communicators change (process-grid search), because a new group starts at epoch 0 while the
     // flag rows of its channel may still hold the last epoch of a differently composed group.
@@ -94,12 +90,6 @@ private:
     };
     int open_all(const void* base, size_t offset, Slot& s);
     Group* group_for(const std::vector<int>& members, int channel, int* rc);
-    struct SyncEntry {
-        FusedSync* d_state = nullptr;
-        unsigned int* d_tickets = nullptr;
-    };
-    std::map<std::pair<int, std::vector<int>>, SyncEntry> syncs_;
-    void free_syncs();
 
     Comm world_;
     bool inited_ = false, available_ = false, shared_device_ = false;

@@ -1595,17 +1595,9 @@ long long Plan::handle_evictions() const {
 
 bool Plan::graphs_usable() const {
     if (!graphs_enabled_) return false;
-    // NCCL collectives are left out of graphs by default (user-buffer registration, proxy threads);
-    // DTFFTB_GRAPHS_NCCL=1 captures them too (ncclSend/ncclRecv and the pipelined backend's
-    // event fork/join are capturable) -- opt-in until it has been measured on a multi-GPU box.
-    static const bool nccl_graphs = [] {
-        const char* e = getenv("DTFFTB_GRAPHS_NCCL");
-        return e && atoi(e) != 0;
-    }();
-    auto ok = [](int b) {
-        return b == BACKEND_NONE || b == BACKEND_NVLINK_FUSED ||
-               (nccl_graphs && (b == BACKEND_NCCL || b == BACKEND_NCCL_PIPELINED));
-    };
+    // NCCL collectives stay out of graphs: capturing them (measured on 2 B200, profiles/r02b_half_ncclgraphs*_n2.jsonl)
+    // changed the launch-bound half-size configs by -1.7 % ... +3 %, not a win worth the user-buffer / proxy-thread caveats
+    auto ok = [](int b) { return b == BACKEND_NONE || b == BACKEND_NVLINK_FUSED; };
     if (comm_.size() > 1 && !ok(backend_)) return false;
     if (comm_.size() > 1 && is_reshape_enabled_ && !ok(reshape_backend_)) return false;
     return true;

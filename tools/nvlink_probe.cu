@@ -169,11 +169,18 @@ __global__ void __launch_bounds__(32) k_tma2tma(const unsigned char* __restrict_
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- local HBM load to run beside a link variant: plain 16-byte copy inside one device -----------------
+__global__ void __launch_bounds__(256) k_local_copy(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
 struct Side {
     int dev;
     unsigned char *src, *dst;  // src is local to dev, dst lives on the OTHER device
-    cudaStream_t stream;
-    cudaEvent_t e0, e1;
+    cudaStream_t stream, bg_stream;
+    cudaEvent_t e0, e1, b0, b1;
+    unsigned char *bg_src, *bg_dst;  // local buffers of the background HBM load
 };
 
 int main(int argc, char** argv) {
@@ -190,6 +197,7 @@ int main(int argc, char** argv) {
         return 0;
     }
     const size_t max_pitch_factor = 8;
+    const size_t bg_bytes = 1ull << 30;
     Side side[2];
     unsigned char* bufs[2][2];
     for (int d = 0; d < 2; ++d) {
@@ -205,8 +213,14 @@ int main(int argc, char** argv) {
         side[d].src = bufs[d][0];
         side[d].dst = bufs[1 - d][1];
         CK(cudaStreamCreateWithFlags(&side[d].stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&side[d].bg_stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&side[d].e0));
         CK(cudaEventCreate(&side[d].e1));
+        CK(cudaEventCreate(&side[d].b0));
+        CK(cudaEventCreate(&side[d].b1));
+        CK(cudaMalloc(&side[d].bg_src, bg_bytes));
+        CK(cudaMalloc(&side[d].bg_dst, bg_bytes));
+        CK(cudaMemset(side[d].bg_src, 7, bg_bytes));
     }
     int sms = 148;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -229,6 +243,10 @@ int main(int argc, char** argv) {
         }
     }
     vars.push_back({"memcpy", 0, 1, 0});
+    for (int run : {512, 1024, 2048, 4096}) {
+        vars.push_back({"memcpy2d", run, 8, 0});
+        vars.push_back({"memcpy3d", run, 8, 512});  // planes of 512 rows, like one y-plane of the 512^3 Z pencil
+    }
 
     auto launch = [&](const Var& v, Side& s) {
         CK(cudaSetDevice(s.dev));
@@ -239,6 +257,21 @@ int main(int argc, char** argv) {
         }
         const long long nrows = (long long)(bytes / v.run);
         const long long pitch = (long long)v.run * v.pitch_mul;
+        if (v.name == "memcpy2d") {  // copy engine, rows of `run` bytes at the destination pitch
+            CK(cudaMemcpy2DAsync(s.dst, (size_t)pitch, s.src, (size_t)v.run, (size_t)v.run, (size_t)nrows,
+                                 cudaMemcpyDeviceToDevice, s.stream));
+            return;
+        }
+        if (v.name == "memcpy3d") {
+            cudaMemcpy3DPeerParms p3{};
+            const size_t rows = (size_t)v.param, planes = (size_t)nrows / rows;
+            p3.srcDevice = s.dev, p3.dstDevice = 1 - s.dev;
+            p3.srcPtr = make_cudaPitchedPtr(s.src, (size_t)v.run, (size_t)v.run, rows);
+            p3.dstPtr = make_cudaPitchedPtr(s.dst, (size_t)pitch, (size_t)v.run, rows);
+            p3.extent = make_cudaExtent((size_t)v.run, rows, planes);
+            CK(cudaMemcpy3DPeerAsync(&p3, s.stream));
+            return;
+        }
         if (v.name == "st128") {
             k_st128<8><<<sms * v.param, 256, 0, s.stream>>>((const uint4*)s.src, (uint4*)s.dst, n16, v.run / 16, pitch / 16);
         } else if (v.name == "pull128") {
@@ -275,8 +308,12 @@ int main(int argc, char** argv) {
         CK(cudaGetLastError());
     };
 
-    for (int bidir = 0; bidir < 2; ++bidir) {
+    for (int pass = 0; pass < 3; ++pass) {
+        const int bidir = pass >= 1 ? 1 : 0;
+        const bool with_bg = pass == 2;  // both directions busy AND a local HBM copy running on every device
         for (const Var& v : vars) {
+            if (with_bg && !(v.name == "memcpy" || ((v.name == "st128" || v.name == "memcpy2d" || v.name == "memcpy3d") && v.run == 1024 && v.pitch_mul == 8)))
+                continue;
             const int nsides = bidir ? 2 : 1;
             for (int w = 0; w < 2; ++w)
                 for (int d = 0; d < nsides; ++d) launch(v, side[d]);
@@ -284,6 +321,16 @@ int main(int argc, char** argv) {
                 CK(cudaSetDevice(d));
                 CK(cudaDeviceSynchronize());
             }
+            const int bg_iters = 3 * iters;
+            if (with_bg)
+                for (int d = 0; d < 2; ++d) {
+                    CK(cudaSetDevice(d));
+                    CK(cudaEventRecord(side[d].b0, side[d].bg_stream));
+                    for (int it = 0; it < bg_iters; ++it)
+                        k_local_copy<<<sms * 8, 256, 0, side[d].bg_stream>>>((const uint4*)side[d].bg_src, (uint4*)side[d].bg_dst,
+                                                                              (long long)(bg_bytes / 16));
+                    CK(cudaEventRecord(side[d].b1, side[d].bg_stream));
+                }
             for (int d = 0; d < nsides; ++d) {
                 CK(cudaSetDevice(d));
                 CK(cudaEventRecord(side[d].e0, side[d].stream));
@@ -303,9 +350,22 @@ int main(int argc, char** argv) {
                 if (ms > worst) worst = ms;
             }
             const double gbs = (double)bytes * iters / (worst * 1e-3) / 1e9;
+            double bg_gbs = 0.0;
+            if (with_bg) {
+                float bg_worst = 0.f;
+                for (int d = 0; d < 2; ++d) {
+                    CK(cudaSetDevice(d));
+                    CK(cudaEventSynchronize(side[d].b1));
+                    float ms = 0.f;
+                    CK(cudaEventElapsedTime(&ms, side[d].b0, side[d].b1));
+                    if (ms > bg_worst) bg_worst = ms;
+                }
+                // read + write bytes of the local copy over ITS whole run (part of it alone, after the link variant ended)
+                bg_gbs = 2.0 * (double)bg_bytes * bg_iters / (bg_worst * 1e-3) / 1e9;
+            }
             printf("{\"variant\": \"%s\", \"run_bytes\": %d, \"pitch_mul\": %d, \"param\": %d, \"bidir\": %d, \"mb\": %zu, "
-                   "\"ms\": %.4f, \"GBps_per_direction\": %.1f}\n",
-                   v.name.c_str(), v.run, v.pitch_mul, v.param, bidir, bytes >> 20, worst / iters, gbs);
+                   "\"ms\": %.4f, \"GBps_per_direction\": %.1f, \"with_local_hbm_load\": %d, \"local_copy_GBps_over_its_run\": %.1f}\n",
+                   v.name.c_str(), v.run, v.pitch_mul, v.param, bidir, bytes >> 20, worst / iters, gbs, with_bg ? 1 : 0, bg_gbs);
             fflush(stdout);
         }
     }

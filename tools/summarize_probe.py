@@ -8,6 +8,10 @@ for r in rows:
     if "variant" not in r:
         print(r)
         continue
+    if r.get("with_local_hbm_load"):
+        print("WITH LOCAL HBM LOAD:", r["variant"], r["run_bytes"], "link", r["GBps_per_direction"], "GB/s/dir; local copy",
+              r["local_copy_GBps_over_its_run"], "GB/s over its run")
+        continue
     k = (r["variant"], r["run_bytes"], r["pitch_mul"], r["bidir"])
     if k not in best or r["GBps_per_direction"] > best[k][0]:
         best[k] = (r["GBps_per_direction"], r["param"])
