@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
                                                 C.POINTER(C.c_float), C.POINTER(C.c_double)]
     L.dtfftb_kernel_autotune_report.restype = C.c_int
     L.dtfftb_kernel_create_dry.argtypes = [C.POINTER(vp), C.c_int, i32p, C.c_int, C.c_int64, i32p, C.c_int]
+    L.dtfftb_kernel_create_boxes.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.c_int, i64p, C.POINTER(vp)]
+    L.dtfftb_kernel_create_boxes.restype = C.c_int
     L.dtfftb_kernel_create_boxes_dry.argtypes = [C.POINTER(vp), C.c_int, C.c_int64, C.c_int, i64p, C.c_int]
     L.dtfftb_kernel_dump_table.argtypes = [vp, C.c_int, C.c_int, C.c_int32, i64p, i32p, i64p, i32p]
     for name in ("dtfftb_kernel_create_dry", "dtfftb_kernel_create_boxes_dry", "dtfftb_kernel_dump_table"):
@@ -143,6 +145,8 @@ def _declare_plan_api(L):
                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
         "dtfftb_plan_describe_chunk": [vp, C.c_int, C.c_int32, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)],
+        "dtfftb_plan_describe_dma": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, C.POINTER(C.c_int64)],
+        "dtfftb_plan_describe_peer_piece": [vp, C.c_int, C.c_int, C.c_int, C.c_int32, C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_local_piece": [vp, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, i32p,
                                              C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_reshape": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, C.POINTER(C.c_int64),

@@ -380,6 +380,62 @@ Box intersect_box_clipped(const RankLayout& src, const RankLayout& dst, const lo
 }
 }  // namespace
 
+DmaBlock dma_block(const Box& b, bool transposing, long long staging_off) {
+    DmaBlock d;
+    if (b.empty()) {
+        d.ok = true;  // nothing to move
+        return d;
+    }
+    // destination view: a contiguous run and two outer axes (extent, stride)
+    long long run, nA, sA, nB, sB;
+    if (transposing) {  // family T: output contiguous along b
+        run = b.n1, nA = b.n0, sA = b.os0, nB = b.n2, sB = b.os2;
+    } else {  // family R: output contiguous along a
+        run = b.n0, nA = b.n1, sA = b.os1, nB = b.n2, sB = b.os2;
+    }
+    bool a_is_rows = true;  // rows = axis A, planes = axis B
+    if (nA == 1 && nB > 1) a_is_rows = false;
+    if (nA > 1 && nB > 1 && sB < sA) a_is_rows = false;
+    const long long n_rows = a_is_rows ? nA : nB, s_rows = a_is_rows ? sA : sB;
+    const long long n_planes = a_is_rows ? nB : nA, s_planes = a_is_rows ? sB : sA;
+    d.run = run, d.rows = n_rows, d.planes = n_planes;
+    d.dst_off = b.out_off;
+    d.dst_pitch = n_rows > 1 ? s_rows : run;
+    if (n_planes > 1) {
+        if (d.dst_pitch <= 0 || s_planes % d.dst_pitch != 0 || s_planes / d.dst_pitch < n_rows) return d;  // ok = false
+        d.dst_plane_rows = s_planes / d.dst_pitch;
+    } else {
+        d.dst_plane_rows = n_rows;
+    }
+    if (d.dst_pitch < run) return d;
+    // pack: same source box, destination = dense [planes][rows][run] at staging_off
+    d.pack = b;
+    d.pack.out_off = staging_off;
+    const long long st_rows = run, st_planes = run * n_rows;
+    if (transposing) {
+        d.pack.os1 = 1;
+        d.pack.os0 = a_is_rows ? st_rows : st_planes;
+        d.pack.os2 = a_is_rows ? st_planes : st_rows;
+    } else {
+        d.pack.os0 = 1;
+        d.pack.os1 = a_is_rows ? st_rows : st_planes;
+        d.pack.os2 = a_is_rows ? st_planes : st_rows;
+    }
+    d.ok = true;
+    return d;
+}
+
+Box local_box_for_peer(const Pencil& send, const Pencil& recv, const Pencil& next_of_peer) {
+    const RankLayout src = layout_of(send), dst = layout_of(recv), nxt = layout_of(next_of_peer);
+    long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
+    for (int j = 0; j < nxt.ndims; ++j) {
+        clip[nxt.axis[j]][0] = nxt.starts[j];
+        clip[nxt.axis[j]][1] = (long long)nxt.starts[j] + nxt.counts[j];
+    }
+    bool tr = false;
+    return intersect_box_clipped(src, dst, clip, &tr);
+}
+
 Box local_producer_box(const Pencil& send, const Pencil& recv, int k, int nchunks) {
     const int nd = recv.ndims;
     const RankLayout src = layout_of(send), dst = layout_of(recv);

@@ -137,6 +137,31 @@ Box local_producer_box(const Pencil& send, const Pencil& recv, int k, int nchunk
 std::vector<Box> local_consumer_boxes(const Pencil& send, const Pencil& recv, const std::vector<Pencil>& senders_src,
                                       int k, int nchunks);
 
+// ---- copy-engine form of a direct-store block (handle.h, DMA mode) ------------------------------
+// On B200 a kernel's remote stores leave as 128-byte NVLink writes and top out near 690 GB/s per direction,
+// and they collapse (to ~420 GB/s) when an HBM-bound kernel runs beside them; a copy engine moves the same
+// rows -- even 1 KB rows at an 8 KB pitch -- at 735-755 GB/s and keeps ~640 GB/s under that load
+// (profiles/r02c_nvlink_probe_n2.md).  So a peer block can travel as: a LOCAL pack of the block in the order
+// of its destination rows (one pass through HBM), then ONE strided 3-D copy that deposits every row at its
+// final address in the peer's array (no unpack).  `pack` = the block's source box with packed destination
+// strides (relative to the staging buffer, block at `staging_off`); the copy moves `planes` x `rows` rows of
+// `run` elements from the staging block (dense) to dst_off + row * dst_pitch + plane * dst_plane_rows *
+// dst_pitch.  ok == false: the block's two outer destination strides are not multiples of one another, it
+// cannot be one pitched 3-D copy.
+struct DmaBlock {
+    Box pack;
+    long long run = 0, rows = 0, planes = 0;
+    long long dst_off = 0, dst_pitch = 0, dst_plane_rows = 0;
+    bool ok = false;
+};
+DmaBlock dma_block(const Box& b, bool transposing, long long staging_off);
+
+// The part of a LOCAL transposition `send -> recv` (one rank in its communicator) that writes exactly what
+// member `peer` of the exchanging transposition `recv -> next_by_member[...]` will be sent: the global-index
+// range of `next_by_member[peer]` clipped out of the local transposition.  Lets the local transposition run
+// peer by peer in front of the packs of a DMA-mode exchange (Plan::run_transpose_pair).
+Box local_box_for_peer(const Pencil& send, const Pencil& recv, const Pencil& next_of_peer);
+
 // ---- brick <-> pencil reshape over NCCL: pack -> all-to-all(v) -> unpack -------------------
 // Block (me -> i) is the global-index intersection of my source with i's destination, carried
 // in a contiguous slot in DESTINATION axis order (both sides of a reshape share the axis order,

@@ -12,6 +12,20 @@ namespace dtfftb {
 void ReshapeHandle::destroy() {
     local_pieces_[0].clear();
     local_pieces_[1].clear();
+    peer_pieces_[0].clear();
+    peer_pieces_[1].clear();
+    dma_pack_.reset();
+    dma_self_.reset();
+    dma_blocks_.clear();
+    dma_ = false;
+    dma_bases_ = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (copy_streams_[i]) cudaStreamDestroy(copy_streams_[i]);
+        if (copies_done_[i]) cudaEventDestroy(copies_done_[i]);
+        copy_streams_[i] = nullptr, copies_done_[i] = nullptr;
+    }
+    for (cudaEvent_t e : pack_done_) cudaEventDestroy(e);
+    pack_done_.clear();
     fused_.clear();
     fused_chunks_.clear();
     if (ctx_.peers)
@@ -88,11 +102,55 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
         }
         if (any_t && any_r) return DTFFTB_ERROR_INTERNAL;
         fused_family_ = any_r ? FAM_R : FAM_T;
+        // ---- copy-engine form (handle.h): every member must take the same decision, so it is taken from what
+        // every member knows -- all pencils of the group
+        {
+            bool all_ok = true;
+            long long max_block_bytes = 0;
+            for (int r = 0; r < P && all_ok; ++r) {
+                const RankLayout sr = layout_of(send_by_member[(size_t)r]);
+                for (int i = 0; i < P && all_ok; ++i) {
+                    if (i == r) continue;
+                    bool tr = false;
+                    const Box b = intersect_box(sr, layout_of(recv_by_member[(size_t)i]), &tr);
+                    if (b.empty()) continue;
+                    all_ok = dma_block(b, tr, 0).ok;
+                    max_block_bytes = std::max(max_block_bytes, b.volume() * es_);
+                }
+            }
+            const char* e = getenv("DTFFTB_FUSED_MODE");
+            const bool force_dma = e && (e[0] == 'd' || e[0] == 'D');
+            const bool force_store = e && (e[0] == 's' || e[0] == 'S');
+            // a copy costs a few microseconds of set-up: below ~1 MiB per peer the single direct-store kernel wins
+            dma_ = all_ok && !force_store && (force_dma || max_block_bytes >= (1ll << 20));
+            if (dma_) {
+                dma_blocks_.assign((size_t)P, DmaBlock{});
+                std::vector<Box> packs((size_t)P), selfs((size_t)P);
+                long long off = 0;
+                for (int i = 0; i < P; ++i) {
+                    if (i == me || fused_boxes_[(size_t)i].empty()) {
+                        if (i == me) selfs[(size_t)i] = fused_boxes_[(size_t)i];
+                        dma_blocks_[(size_t)i].ok = true;
+                        continue;
+                    }
+                    dma_blocks_[(size_t)i] = dma_block(fused_boxes_[(size_t)i], fused_family_ == FAM_T, off);
+                    packs[(size_t)i] = dma_blocks_[(size_t)i].pack;
+                    off += fused_boxes_[(size_t)i].volume();
+                }
+                dma_pack_.reset(new Kernel);
+                rc = dma_pack_->create_boxes(fused_family_, es_, packs);
+                if (rc) return rc;
+                dma_self_.reset(new Kernel);
+                rc = dma_self_->create_boxes(fused_family_, es_, selfs);
+                if (rc) return rc;
+                aux_bytes_ = off * es_;  // staging of the blocks that leave the GPU
+            }
+        }
         geo_ = HandleGeometry{};
         geo_.ttype = ttype, geo_.rtype = rtype, geo_.ndims = ndims;
         geo_.comm_size = P, geo_.comm_rank = me, geo_.members = members;
         geo_.has_exchange = true, geo_.is_fused = true;
-        launches_ = 3;  // barrier + fused kernel + barrier
+        launches_ = dma_ ? 2 + P : 3;  // barrier + (packs + self | fused kernel) + barrier
         created_ = true;
         return DTFFT_SUCCESS;
     }
@@ -195,6 +253,126 @@ int ReshapeHandle::peer_bases(void* out, std::vector<void*>* bases) {
     return DTFFT_SUCCESS;
 }
 
+int ReshapeHandle::ensure_dma_resources() {
+    cudaError_t ce;
+    for (int i = 0; i < 2; ++i) {
+        if (!copy_streams_[i]) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            ce = cudaStreamCreateWithPriority(&copy_streams_[i], cudaStreamNonBlocking, hi);
+            if (ce != cudaSuccess) return cuda_error(ce);
+            ce = cudaEventCreateWithFlags(&copies_done_[i], cudaEventDisableTiming);
+            if (ce != cudaSuccess) return cuda_error(ce);
+        }
+    }
+    while (pack_done_.size() < members_.size()) {
+        cudaEvent_t e;
+        ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        pack_done_.push_back(e);
+    }
+    return DTFFT_SUCCESS;
+}
+
+int ReshapeHandle::dma_begin(void* out, cudaStream_t stream) {
+    if (!dma_mode()) return DTFFTB_ERROR_INTERNAL;
+    int rc = ensure_dma_resources();
+    if (rc) return rc;
+    std::vector<void*> bases;
+    rc = peer_bases(out, &bases);  // collective on the first use of `out`; an identity check afterwards
+    if (rc) return rc;
+    dma_bases_ = &maps_.find(out)->second.bases;
+    copy_used_[0] = copy_used_[1] = false;
+    copy_turn_ = 0;
+    return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1), stream);  // every member's `out` is free
+}
+
+int ReshapeHandle::dma_send(const void* in, void* out, void* aux, int peer, cudaStream_t stream) {
+    (void)out;
+    if (!dma_mode() || !dma_bases_ || peer < 0 || peer >= (int)members_.size() || peer == me_) return DTFFTB_ERROR_INTERNAL;
+    if (!aux) return DTFFT_ERROR_INVALID_AUX;
+    const DmaBlock& d = dma_blocks_[(size_t)peer];
+    if (d.run <= 0 || fused_boxes_[(size_t)peer].empty()) return DTFFT_SUCCESS;
+    int rc = dma_pack_->execute(in, aux, stream, peer + 1, false);  // block -> staging, in destination row order
+    if (rc) return rc;
+    cudaError_t ce = cudaEventRecord(pack_done_[(size_t)peer], stream);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    const int c = copy_turn_++ & 1;
+    cudaStream_t cs = copy_streams_[c];
+    copy_used_[c] = true;
+    ce = cudaStreamWaitEvent(cs, pack_done_[(size_t)peer], 0);
+    if (ce != cudaSuccess) return cuda_error(ce);
+    cudaMemcpy3DParms p{};
+    const size_t row_bytes = (size_t)(d.run * es_);
+    p.srcPtr = make_cudaPitchedPtr(static_cast<char*>(aux) + (size_t)(d.pack.out_off * es_), row_bytes, row_bytes, (size_t)d.rows);
+    p.dstPtr = make_cudaPitchedPtr(static_cast<char*>((*dma_bases_)[(size_t)peer]) + (size_t)(d.dst_off * es_),
+                                   (size_t)(d.dst_pitch * es_), row_bytes, (size_t)d.dst_plane_rows);
+    p.extent = make_cudaExtent(row_bytes, (size_t)d.rows, (size_t)d.planes);
+    p.kind = cudaMemcpyDefault;
+    ce = cudaMemcpy3DAsync(&p, cs);  // one strided copy deposits every row at its final address in the peer's array
+    return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
+}
+
+int ReshapeHandle::dma_self(const void* in, void* out, cudaStream_t stream) {
+    if (!dma_mode()) return DTFFTB_ERROR_INTERNAL;
+    return dma_self_->execute_all(in, out, stream);
+}
+
+// Tell `peer` that my block has landed in its array: enqueued on the copy stream that carried it.
+int ReshapeHandle::dma_signal(int peer) {
+    if (!dma_mode() || peer < 0 || peer >= (int)members_.size() || peer == me_) return DTFFTB_ERROR_INTERNAL;
+    // the copy of `peer` was the last one enqueued on its stream
+    const int c = (copy_turn_ - 1) & 1;
+    return ctx_.peers->signal(members_, 6 + (comm_id_ - 1), peer, copy_streams_[c]);
+}
+
+int ReshapeHandle::dma_wait(int source, cudaStream_t stream) {
+    if (!dma_mode() || source < 0 || source >= (int)members_.size() || source == me_) return DTFFTB_ERROR_INTERNAL;
+    return ctx_.peers->wait(members_, 6 + (comm_id_ - 1), source, stream);
+}
+
+int ReshapeHandle::dma_end(cudaStream_t stream, bool landed_barrier) {
+    if (!dma_mode()) return DTFFTB_ERROR_INTERNAL;
+    for (int c = 0; c < 2; ++c) {
+        if (!copy_used_[c]) continue;
+        cudaError_t ce = cudaEventRecord(copies_done_[c], copy_streams_[c]);
+        if (ce != cudaSuccess) return cuda_error(ce);
+        ce = cudaStreamWaitEvent(stream, copies_done_[c], 0);
+        if (ce != cudaSuccess) return cuda_error(ce);
+    }
+    dma_bases_ = nullptr;
+    if (!landed_barrier) return DTFFT_SUCCESS;
+    return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1) + 1, stream);  // every block has landed
+}
+
+int ReshapeHandle::execute_dma(void* in, void* out, cudaStream_t stream, void* aux) {
+    const int P = (int)members_.size();
+    int rc = dma_begin(out, stream);
+    if (rc) return rc;
+    for (int k = 1; k < P; ++k) {  // rotated order: at any time every member receives from one peer
+        rc = dma_send(in, out, aux, (me_ + k) % P, stream);
+        if (rc) return rc;
+    }
+    rc = dma_self(in, out, stream);  // local HBM work beside the copies
+    if (rc) return rc;
+    return dma_end(stream, true);
+}
+
+int ReshapeHandle::local_piece(const void* in, void* out, int side, int peer, const std::vector<Pencil>& other_by_member,
+                               cudaStream_t stream) {
+    if (!is_local_transpose() || (side != 0 && side != 1) || peer < 0 || peer >= (int)other_by_member.size())
+        return DTFFTB_ERROR_INTERNAL;
+    auto it = peer_pieces_[side].find(peer);
+    if (it == peer_pieces_[side].end()) {
+        std::unique_ptr<Kernel> k(new Kernel);
+        const std::vector<Box> one = {local_box_for_peer(send_, recv_by_member_[(size_t)me_], other_by_member[(size_t)peer])};
+        int rc = k->create_boxes(FAM_T, es_, one);
+        if (rc) return rc;
+        it = peer_pieces_[side].emplace(peer, std::move(k)).first;
+    }
+    return it->second->execute_all(in, out, stream);
+}
+
 int ReshapeHandle::execute_fused(void* in, void* out, cudaStream_t stream) {
     PeerRegistry& peers = *ctx_.peers;
     std::vector<void*> bases;
@@ -294,7 +472,7 @@ int ReshapeHandle::local_consume(const void* in, void* out, int k, int nchunks, 
 int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (!has_exchange_) return pack_->execute(in, out, stream, 0, false);
-    if (backend_ == BACKEND_NVLINK_FUSED) return execute_fused(in, out, stream);
+    if (backend_ == BACKEND_NVLINK_FUSED) return dma_ ? execute_dma(in, out, stream, aux) : execute_fused(in, out, stream);
     int rc;
     if (nccl_->is_pipelined()) {
         if (!aux) return DTFFT_ERROR_INVALID_AUX;

@@ -113,6 +113,33 @@ public:
     // "All members' chunk has landed" between the chunks of a chunked exchange (consumer pipelining).
     int fused_chunk_landed(cudaStream_t stream) { return fused_end(stream); }
 
+    // ---- NVLINK_FUSED, copy-engine form of the exchange (geometry.h: DmaBlock) ----------------------------
+    // Each peer block is packed locally in the order of its destination rows (workspace: `aux`, aux_bytes()) and
+    // deposited at its final address in the peer's `out` by ONE strided 3-D copy on a copy engine; the self block
+    // is a plain local kernel.  Same barriers, same result as the direct-store kernel, but the link runs at the
+    // copy engines' 735-755 GB/s instead of the ~680 GB/s of SM stores and keeps its rate while SM kernels use
+    // the HBM, so the local transposition next to it can run beside it.  The pieces, for Plan::run_transpose_pair:
+    //     dma_begin(out, s)            map the members' `out`, "every member's `out` is free" barrier
+    //     dma_send(in, out, aux, p, s) pack block p (stream s), then its copy on a copy stream
+    //     dma_self(in, out, s)         my own block
+    //     dma_signal(p) / dma_wait(r, s)  per-pair "block has landed" flags instead of the group barrier
+    //     dma_end(s, barrier)          join the copy streams (+ "all landed" barrier)
+    bool dma_mode() const { return created_ && has_exchange_ && backend_ == BACKEND_NVLINK_FUSED && dma_; }
+    int dma_begin(void* out, cudaStream_t stream);
+    int dma_send(const void* in, void* out, void* aux, int peer, cudaStream_t stream);
+    int dma_self(const void* in, void* out, cudaStream_t stream);
+    int dma_advance_signals(cudaStream_t stream) { return ctx_.peers->advance_epoch(members_, 6 + (comm_id_ - 1), stream); }
+    int dma_signal(int peer);
+    int dma_wait(int source, cudaStream_t stream);
+    int dma_end(cudaStream_t stream, bool landed_barrier);
+    int n_members() const { return (int)members_.size(); }
+    int my_index() const { return me_; }
+    const std::vector<Pencil>& recv_by_member() const { return recv_by_member_; }
+    // Pieces of a LOCAL transposition cut by the members of the exchange next to it (geometry.h: local_box_for_peer):
+    // piece `peer` writes (side 0, the exchange follows) or reads (side 1, the exchange precedes) exactly the elements
+    // that travel between me and `peer` in that exchange.
+    int local_piece(const void* in, void* out, int side, int peer, const std::vector<Pencil>& other_by_member, cudaStream_t stream);
+
 private:
     int execute_fused(void* in, void* out, cudaStream_t stream);
     // piece kernels of a local transposition: [0] producer side, [1] consumer side, keyed by nchunks
@@ -150,6 +177,21 @@ private:
         unsigned long long id = 0;  // buffer_id(out) when it was published
     };
     std::map<const void*, PeerMap> maps_;
+    // copy-engine form
+    bool dma_ = false;
+    std::vector<DmaBlock> dma_blocks_;      // per member
+    std::unique_ptr<Kernel> dma_pack_;      // in -> staging, one launch per peer
+    std::unique_ptr<Kernel> dma_self_;      // my own block, in -> out
+    cudaStream_t copy_streams_[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> pack_done_;    // per member
+    cudaEvent_t copies_done_[2] = {nullptr, nullptr};
+    bool copy_used_[2] = {false, false};
+    int copy_turn_ = 0;
+    const std::vector<void*>* dma_bases_ = nullptr;  // of the `out` of the exchange in flight (dma_begin)
+    int execute_dma(void* in, void* out, cudaStream_t stream, void* aux);
+    int ensure_dma_resources();
+    // local pieces cut by the members of a neighbouring exchange: [side] keyed by member
+    std::map<int, std::unique_ptr<Kernel>> peer_pieces_[2];
 };
 
 }  // namespace dtfftb

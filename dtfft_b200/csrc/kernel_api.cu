@@ -85,6 +85,29 @@ int dtfftb_kernel_create_boxes_dry(dtfftb_kernel_t* kernel, int family, int64_t 
     return DTFFT_SUCCESS;
 }
 
+int dtfftb_kernel_create_boxes(dtfftb_kernel_t* kernel, int family, int64_t base_storage, int n_boxes,
+                               const int64_t* boxes, void* const* out_bases) {
+    if (!kernel || !boxes || n_boxes <= 0) return DTFFT_ERROR_INVALID_USAGE;
+    *kernel = nullptr;
+    dtfftb_kernel_s* h = new (std::nothrow) dtfftb_kernel_s;
+    if (!h) return DTFFT_ERROR_ALLOC_FAILED;
+    std::vector<dtfftb::Box> bx((size_t)n_boxes);
+    for (int i = 0; i < n_boxes; ++i) {
+        const int64_t* o = boxes + 10 * i;
+        dtfftb::Box& b = bx[(size_t)i];
+        b.n0 = o[0], b.n1 = o[1], b.n2 = o[2], b.in_off = o[3], b.out_off = o[4];
+        b.is1 = o[5], b.is2 = o[6], b.os0 = o[7], b.os1 = o[8], b.os2 = o[9];
+    }
+    int rc = h->k.create_boxes((dtfftb::Family)family, base_storage, bx);
+    if (rc == DTFFT_SUCCESS && out_bases && !h->k.is_noop()) rc = h->k.set_peer_out(out_bases, nullptr);
+    if (rc != DTFFT_SUCCESS) {
+        delete h;
+        return rc;
+    }
+    *kernel = h;
+    return DTFFT_SUCCESS;
+}
+
 int dtfftb_kernel_dump_table(dtfftb_kernel_t kernel, int unit, int neighbor, int32_t cap, int64_t* rows,
                              int32_t* n_blocks, int64_t* total_items, int32_t* launch) {
     if (!kernel || !n_blocks || !total_items || !launch) return DTFFT_ERROR_INVALID_USAGE;

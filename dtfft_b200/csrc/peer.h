@@ -58,6 +58,14 @@ public:
     // Enqueue a barrier among `members` (world ranks, must contain me) on `stream`.
     // `channel` separates independent groups (1-D communicator id 1..3, x2 phases).
     int barrier(const std::vector<int>& members, int channel, cudaStream_t stream);
+    // Pairwise "landed" flags (copy-engine exchange with a consumer right behind it): one epoch counter per
+    // (members, channel) in device memory, advanced once per exchange by advance_epoch(); signal() stores the
+    // current epoch into flag [channel][me] of ONE member (enqueue it behind the copy that carries the data),
+    // wait() spins until flag [channel][source] of mine has reached the current epoch.  Every member runs the same
+    // sequence of exchanges, so the epochs agree; all three are graph-replayable like barrier().
+    int advance_epoch(const std::vector<int>& members, int channel, cudaStream_t stream);
+    int signal(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream);
+    int wait(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream);
     // Collective.  Forget every barrier group and zero the flags: must be called when the 1-D
     // communicators change (process-grid search), because a new group starts at epoch 0 while the
     // flag rows of its channel may still hold the last epoch of a differently composed group.

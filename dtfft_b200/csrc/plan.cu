@@ -62,6 +62,7 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     if (const char* e = getenv("DTFFTB_OVERLAP_CHUNKS")) overlap_chunks_ = std::max(1, atoi(e)), overlap_user_set_ = true;
     if (const char* e = getenv("DTFFTB_OVERLAP_CTAS")) overlap_ctas_ = std::max(0, atoi(e));
     if (const char* e = getenv("DTFFTB_TRANSPOSE_OVERLAP")) transpose_overlap_ = std::max(1, atoi(e));
+    if (const char* e = getenv("DTFFTB_PAIR_OVERLAP")) pair_overlap_ = atoi(e) != 0;
     if (const char* e = getenv("DTFFTB_GRAPHS")) graphs_enabled_ = atoi(e) != 0;
     is_transpose_plan_ = executor == DTFFT_EXECUTOR_NONE;
     if (kind == PLAN_R2R) {
@@ -1297,7 +1298,7 @@ int Plan::run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void
     stat_launches_ += 2 + nch;
     stat_local_ += h.local_elements() * base_storage_;
     stat_remote_ += h.remote_elements() * base_storage_;
-    stat_overlapped_ += 1;
+    stat_overlapped_ += 1, stat_eager_only_ += 1;
     return DTFFT_SUCCESS;
 }
 
@@ -1351,6 +1352,78 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
     if (i1 == handles_.end() || i2 == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
     ReshapeHandle &h1 = *i1->second, &h2 = *i2->second;
     const bool distinct = a != b && b != c && a != c;
+    // Copy-engine exchanges pipeline PEER BY PEER with the local transposition next to them (the copies keep their
+    // rate while SM kernels use the HBM, profiles/r02c_nvlink_probe_n2.md; the direct-store kernel does not):
+    //   producer: [local piece for peer p -> pack p] on the plan stream, copy p on a copy stream, for every peer;
+    //   consumer: as each sender's block lands (pairwise flag behind its copy) the local piece that reads it runs.
+    // (every member must take the same path: nobody may be without data)
+    if (pair_overlap_ && distinct && aux && h1.is_local_transpose() && h2.dma_mode() && h2.min_member_slow_extent() > 0) {
+        TraceRange trace("Transpose pair (local pieces -> packs || copies)", kColorTranspose);
+        const int P = h2.n_members(), me = h2.my_index();
+        int rc = h2.dma_begin(c, stream_);
+        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
+            rc = run_transpose(t1, a, b, aux);
+            if (rc) return rc;
+            return run_transpose(t2, b, c, aux);
+        }
+        if (rc) return rc;
+        for (int k = 1; k < P; ++k) {
+            const int p = (me + k) % P;
+            rc = h1.local_piece(a, b, 0, p, h2.recv_by_member(), stream_);
+            if (rc) return rc;
+            rc = h2.dma_send(b, c, aux, p, stream_);
+            if (rc) return rc;
+        }
+        rc = h1.local_piece(a, b, 0, me, h2.recv_by_member(), stream_);
+        if (rc) return rc;
+        rc = h2.dma_self(b, c, stream_);
+        if (rc) return rc;
+        rc = h2.dma_end(stream_, true);
+        if (rc) return rc;
+        stat_launches_ += 2 + 3 * P;
+        stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
+        stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
+        stat_overlapped_ += 1;
+        return DTFFT_SUCCESS;
+    }
+    if (pair_overlap_ && distinct && aux && h1.dma_mode() && h2.is_local_transpose() && h1.min_member_slow_extent() > 0) {
+        TraceRange trace("Transpose pair (packs || copies -> local pieces)", kColorTranspose);
+        const int P = h1.n_members(), me = h1.my_index();
+        int rc = h1.dma_begin(b, stream_);
+        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
+            rc = run_transpose(t1, a, b, aux);
+            if (rc) return rc;
+            return run_transpose(t2, b, c, aux);
+        }
+        if (rc) return rc;
+        rc = h1.dma_advance_signals(stream_);  // new epoch of the pairwise "landed" flags, before any copy is enqueued
+        if (rc) return rc;
+        for (int k = 1; k < P; ++k) {
+            const int p = (me + k) % P;
+            rc = h1.dma_send(a, b, aux, p, stream_);
+            if (rc) return rc;
+            rc = h1.dma_signal(p);
+            if (rc) return rc;
+        }
+        rc = h1.dma_self(a, b, stream_);
+        if (rc) return rc;
+        rc = h2.local_piece(b, c, 1, me, h1.send_by_member(), stream_);
+        if (rc) return rc;
+        for (int k = 1; k < P; ++k) {  // sender (me - k) has me as its k-th target: blocks arrive in this order
+            const int r = (me - k + P) % P;
+            rc = h1.dma_wait(r, stream_);
+            if (rc) return rc;
+            rc = h2.local_piece(b, c, 1, r, h1.send_by_member(), stream_);
+            if (rc) return rc;
+        }
+        rc = h1.dma_end(stream_, false);  // my copies are done with the staging buffer; no group barrier needed
+        if (rc) return rc;
+        stat_launches_ += 1 + 5 * P;
+        stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
+        stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
+        stat_overlapped_ += 1;
+        return DTFFT_SUCCESS;
+    }
     long long nch = transpose_overlap_;
     int mode = 0;  // 1 = producer, 2 = consumer
     if (nch > 1 && distinct && h1.is_local_transpose() && h2.can_chunk()) {
@@ -1436,7 +1509,7 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
     }
     stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
     stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
-    stat_overlapped_ += 1;
+    stat_overlapped_ += 1, stat_eager_only_ += 1;
     return DTFFT_SUCCESS;
 }
 
@@ -1453,6 +1526,48 @@ int Plan::describe_local_piece(int t_local, int t_exchange, int side, int k, int
         boxes->push_back(local_producer_box(hl.send[0], hl.recv[0], k, nchunks));
     else
         *boxes = local_consumer_boxes(hl.send[0], hl.recv[0], hx.send, k, nchunks);
+    return DTFFT_SUCCESS;
+}
+
+// Introspection for host tests: the copy-engine form of one transposition on this rank (geometry.h: DmaBlock)
+// and the pieces of a local transposition cut by the members of the exchange next to it.
+int Plan::describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaBlock>* blocks, std::vector<Box>* fused) const {
+    HandleSpec hs;
+    int rc = handle_spec(ttype, &hs);
+    if (rc) return rc;
+    if (members) *members = hs.members;
+    if (me) *me = hs.me;
+    blocks->clear();
+    fused->clear();
+    const RankLayout src = layout_of(hs.send[(size_t)hs.me]);
+    long long off = 0;
+    for (size_t i = 0; i < hs.members.size(); ++i) {
+        bool tr = false;
+        const Box b = intersect_box(src, layout_of(hs.recv[i]), &tr);
+        fused->push_back(b);
+        if ((int)i == hs.me || b.empty()) {
+            DmaBlock d;
+            d.ok = true;
+            blocks->push_back(d);
+            continue;
+        }
+        blocks->push_back(dma_block(b, tr, off));
+        off += b.volume();
+    }
+    return DTFFT_SUCCESS;
+}
+
+int Plan::describe_peer_piece(int t_local, int t_exchange, int side, int peer, Box* box) const {
+    if (side != 0 && side != 1) return DTFFT_ERROR_INVALID_USAGE;
+    HandleSpec hl, hx;
+    int rc = handle_spec(t_local, &hl);
+    if (rc) return rc;
+    rc = handle_spec(t_exchange, &hx);
+    if (rc) return rc;
+    if (hl.members.size() != 1) return DTFFT_ERROR_INVALID_USAGE;  // not a local transposition
+    if (peer < 0 || peer >= (int)hx.members.size()) return DTFFT_ERROR_INVALID_USAGE;
+    // side 0: the exchange follows, cut by the members' DESTINATION pencils; side 1: it precedes, cut by their SOURCES
+    *box = local_box_for_peer(hl.send[0], hl.recv[0], side == 0 ? hx.recv[(size_t)peer] : hx.send[(size_t)peer]);
     return DTFFT_SUCCESS;
 }
 
@@ -1513,7 +1628,7 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
     if (is_transpose_plan_ && kind_ == PLAN_R2C) return DTFFT_ERROR_R2C_EXECUTE_CALLED;
     int rc = check_device_ptrs(in, out, aux);
     if (rc) return rc;
-    stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = 0;
+    stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = stat_eager_only_ = 0;
     void *a1 = nullptr, *a2 = nullptr;
     rc = check_aux(aux, true, &a1, &a2);
     if (rc) return rc;
@@ -1546,7 +1661,7 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
         // A schedule with overlapped stages stays eager: measured on 2 B200 (profiles/r01f_configs_auto_n2.jsonl
         // vs r01d_configs_n2.jsonl, 16384^2 slab) the two-stream pipeline loses its overlap when replayed as
         // graph branches (9.41 ms vs 8.55 ms eager), and such schedules are long enough not to be launch-bound.
-        if (stat_overlapped_ > 0) it->second.failed = true;
+        if (stat_eager_only_ > 0) it->second.failed = true;
         return rc;
     }
     GraphEntry& g = it->second;
@@ -1573,7 +1688,7 @@ int Plan::execute(void* in, void* out, int execute_type, void* aux) {
             cudaGetLastError();
             g.exec = nullptr;
             g.failed = true;
-            stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = 0;
+            stat_launches_ = stat_local_ = stat_remote_ = stat_overlapped_ = stat_eager_only_ = 0;
             return execute_schedule(in, out, fwd, a1, a2, inplace);
         }
         g.launches = stat_launches_, g.local = stat_local_, g.remote = stat_remote_, g.overlapped = stat_overlapped_;

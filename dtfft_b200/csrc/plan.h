@@ -124,6 +124,8 @@ public:
                        long long* chunk_offset) const;
     // Pieces of a LOCAL transposition pipelined with the exchange `t_exchange` next to it (geometry.h:
     // local_producer_box / local_consumer_boxes): side 0 = producer, 1 = consumer.
+    int describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaBlock>* blocks, std::vector<Box>* fused) const;
+    int describe_peer_piece(int t_local, int t_exchange, int side, int peer, Box* box) const;
     int describe_local_piece(int t_local, int t_exchange, int side, int k, int nchunks, std::vector<Box>* boxes) const;
     std::vector<int> transpose_types() const;
 
@@ -228,6 +230,7 @@ private:
     void* aux_ptr_ = nullptr;
     bool is_aux_alloc_ = false;
     int64_t stat_launches_ = 0, stat_local_ = 0, stat_remote_ = 0, stat_overlapped_ = 0;
+    int64_t stat_eager_only_ = 0;  // stages of the last execute whose two-stream pipeline must not be replayed from a graph
     // CUDA-graph replay of dtfft_execute
     struct GraphKey {
         const void *in, *out, *aux;
@@ -252,6 +255,9 @@ private:
     // DTFFTB_TRANSPOSE_OVERLAP=n (opt-in): pipeline a local transposition with the exchanging one next to
     // it in transpose-only schedules (Plan::run_transpose_pair)
     int transpose_overlap_ = 1;
+    // Peer-by-peer pipelining of a local transposition with a copy-engine exchange next to it (run_transpose_pair);
+    // DTFFTB_PAIR_OVERLAP=0 runs the two transpositions one after the other
+    bool pair_overlap_ = true;
     cudaStream_t bar_stream_ = nullptr;
     std::vector<cudaEvent_t> landed_events_;
     cudaEvent_t pair_start_ = nullptr;

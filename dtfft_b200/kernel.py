@@ -121,6 +121,22 @@ class Kernel:
         self.base_storage = int(base_storage)
         return self
 
+    def create_boxes(self, family: int, base_storage, boxes, out_bases=None):
+        """Kernel over explicit boxes on the current device (``dtfftb_kernel_create_boxes``): what the plan's
+        direct-store transpositions run.  ``out_bases``: one destination base per box (device pointers or
+        tensors, may live on a peer GPU with peer access enabled), or None for the launch's ``out``."""
+        self.destroy()
+        bx = np.ascontiguousarray(np.asarray(boxes, dtype=np.int64).reshape(-1, 10))
+        bases = None
+        if out_bases is not None:
+            assert len(out_bases) == bx.shape[0]
+            bases = (C.c_void_p * bx.shape[0])(*[C.c_void_p(_ptr(b) or None) for b in out_bases])
+        _lib.check(_lib.lib().dtfftb_kernel_create_boxes(C.byref(self._h), int(family), int(base_storage), bx.shape[0],
+                                                         bx.ctypes.data_as(C.POINTER(C.c_int64)), bases),
+                   "dtfftb_kernel_create_boxes")
+        self.base_storage = int(base_storage)
+        return self
+
     def dump_table(self, unit=0, neighbor=0) -> dict:
         """Work-item table of one launch of a dry kernel (``dtfftb_kernel_dump_table``)."""
         L = _lib.lib()

@@ -629,6 +629,32 @@ class Plan:
                "dtfftb_plan_describe_local_piece")
         return boxes
 
+    def describe_dma(self, ttype) -> dict:
+        """Copy-engine form of one transposition on this rank (dtfftb_plan_describe_dma): per member the pack box,
+        the strided 3-D copy and the direct-store box of the same block."""
+        import numpy as np
+
+        L = _lib.lib()
+        n, me = C.c_int32(0), C.c_int32(0)
+        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), 0, C.byref(n), C.byref(me), None, None), "dtfftb_plan_describe_dma")
+        members = (C.c_int32 * n.value)()
+        rows = np.zeros((n.value, 27), np.int64)
+        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), n.value, C.byref(n), C.byref(me), members,
+                                          rows.ctypes.data_as(C.POINTER(C.c_int64))), "dtfftb_plan_describe_dma")
+        keys = ("run", "rows", "planes", "dst_off", "dst_pitch", "dst_plane_rows", "ok")
+        return {"members": list(members), "me": me.value, "pack": rows[:, :10].copy(), "fused": rows[:, 17:].copy(),
+                "copy": [dict(zip(keys, (int(v) for v in rows[i, 10:17]))) for i in range(n.value)]}
+
+    def describe_peer_piece(self, t_local, t_exchange, side: int, peer: int):
+        """The piece of a local transposition cut by member ``peer`` of the exchange next to it (one box)."""
+        import numpy as np
+
+        box = np.zeros((1, 10), np.int64)
+        _check(_lib.lib().dtfftb_plan_describe_peer_piece(self._h, int(t_local), int(t_exchange), int(side), int(peer),
+                                                          box.ctypes.data_as(C.POINTER(C.c_int64))),
+               "dtfftb_plan_describe_peer_piece")
+        return box
+
     def describe_reshape(self, type_) -> dict:
         """NCCL-path geometry of one brick <-> pencil reshape on this rank (dtfftb_plan_describe_reshape)."""
         import numpy as np

@@ -116,6 +116,16 @@ int dtfftb_kernel_set_peer_out(dtfftb_kernel_t kernel, void* const* out_bases, c
 /* abstract_kernel%destroy.  Sets *kernel to NULL. */
 int dtfftb_kernel_destroy(dtfftb_kernel_t* kernel);
 
+/* A kernel over explicit boxes -- what the plan layer's direct-store (NVLINK_FUSED) transpositions and brick
+ * reshapes run (the reference's fused backends drive pack_forward / pack_backward per peer from
+ * reshape_handle_generic, src/dtfft_reshape_handle_generic.F90:447; here one launch covers every peer).
+ * `family` 2 = tiled transpose (input contiguous along a, output along b), 3 = row copy; boxes = 10 x n int64:
+ * n0 n1 n2 in_off out_off is1 is2 os0 os1 os2 in elements.  `out_bases` (n pointers or NULL): box i is written
+ * relative to out_bases[i] (a peer-mapped buffer) instead of the launch's `out`; NULL entries mean `out`.
+ * Run it with dtfftb_kernel_execute_all, or box i alone with dtfftb_kernel_execute(neighbor = i + 1). */
+int dtfftb_kernel_create_boxes(dtfftb_kernel_t* kernel, int family, int64_t base_storage, int n_boxes,
+                               const int64_t* boxes, void* const* out_bases);
+
 /* Introspection (used by tests, autotune and `report`). */
 int dtfftb_kernel_get_info(dtfftb_kernel_t kernel, int* family /*0 none,1 copy,2 transpose,3 rows*/,
                            int* unit_bytes, int* tile_a, int* tile_b, int* threads, int64_t* n_items);

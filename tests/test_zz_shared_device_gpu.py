@@ -22,11 +22,13 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_fused_backend_ranks_sharing_one_gpu(cuda, world):
+@pytest.mark.parametrize("world,mode", [(2, "store"), (4, "store"), (2, "dma"), (3, "dma")])
+def test_fused_backend_ranks_sharing_one_gpu(cuda, world, mode):
+    """mode: the direct-store kernel, or every exchange in its copy-engine form (pack + strided 3-D copy per peer,
+    peer-by-peer pair pipelines with pairwise landed flags)."""
     env = dict(os.environ)
     env.update({"DTFFTB_ALLOW_SHARED_DEVICE": "1", "DTFFTB_PEER_TIMEOUT_MS": "20000", "DTFFTB_TEST_EXPERIMENTAL": "1",
-                "OMP_NUM_THREADS": "1"})
+                "DTFFTB_FUSED_MODE": mode, "OMP_NUM_THREADS": "1"})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "_gpu_worker.py")]
