@@ -1,12 +1,18 @@
-# Round 2, 8-GPU call:  gpurun --gpus 8 --timeout 900 -- 'bash tools/r02_n8.sh'
+# Round 2, 8-GPU call:  gpurun --gpus 8 --timeout 1500 -- 'bash tools/r02_n8.sh'   (every minute costs 8 GPU-minutes)
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-# 1. first run of the process-grid search on real GPUs: 512^3 at 8 ranks, 1x8 vs 8x1 vs 2x4 vs 4x2
-DTFFTB_LOG=1 timeout 300 $TR --master-port 29551 tools/grid_search_probe.py > gpurun_out/r02a_grid_search_n8.txt 2>&1; tail -25 gpurun_out/r02a_grid_search_n8.txt
-# 2. multi-GPU suite (fused backend only keeps it short) and the bench line
-DTFFTB_TEST_BACKENDS=NVLINK_FUSED timeout 400 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -15
-timeout 300 $TR --master-port 29552 bench.py --gpus 8 > gpurun_out/r02a_bench_n8.json 2> gpurun_out/r02a_bench_n8.err; cut -c 1-700 gpurun_out/r02a_bench_n8.json; tail -3 gpurun_out/r02a_bench_n8.err
-# 3. (only if the 2-GPU run of DTFFTB_FUSED_SYNC=1 was green) the exchange transposition with folded barriers
-DTFFTB_FUSED_SYNC=1 timeout 300 $TR --master-port 29553 bench.py --gpus 8 > gpurun_out/r02a_bench_n8_fusedsync.json 2> gpurun_out/r02a_bench_n8_fusedsync.err; cut -c 1-700 gpurun_out/r02a_bench_n8_fusedsync.json; tail -3 gpurun_out/r02a_bench_n8_fusedsync.err
-# 4. (only if green at 2 GPUs) local transposition pipelined with the exchange next to it
-for n in 2 4; do DTFFTB_TRANSPOSE_OVERLAP=$n timeout 300 $TR --master-port 2956$n bench.py --gpus 8 > gpurun_out/r02a_bench_n8_pair$n.json 2> gpurun_out/r02a_bench_n8_pair$n.err; cut -c 1-330 gpurun_out/r02a_bench_n8_pair$n.json; tail -2 gpurun_out/r02a_bench_n8_pair$n.err; done
+nvidia-smi -L | head -2
+# 1. the bench line: every backend, parity block first (bit-exact multi-rank parity in the record)
+timeout 400 $TR --master-port 29700 bench.py --gpus 8 > gpurun_out/r02e_bench_n8.json 2> gpurun_out/r02e_bench_n8.err; python tools/show_bench.py gpurun_out/r02e_bench_n8.json; tail -3 gpurun_out/r02e_bench_n8.err
+# 2. A/B of the fused exchange forms
+run() { name=$1; shift; env "$@" timeout 300 $TR --master-port 29701 bench.py --gpus 8 --backend nvlink > gpurun_out/r02e_bench_n8_$name.json 2> gpurun_out/r02e_bench_n8_$name.err; python tools/show_bench.py gpurun_out/r02e_bench_n8_$name.json 2>&1 | head -4; tail -2 gpurun_out/r02e_bench_n8_$name.err; }
+run store DTFFTB_FUSED_MODE=store
+run dma_nopair DTFFTB_FUSED_MODE=dma DTFFTB_PAIR_OVERLAP=0
+run dma_nograph DTFFTB_FUSED_MODE=dma DTFFTB_GRAPHS=0
+# 3. configs C3 / C4 / C5 at full size, per stage against the roofline
+timeout 600 $TR --master-port 29702 tools/configs_profile.py --configs c3,c4,c5 --backends nvlink,nccl > gpurun_out/r02e_configs_profile_n8.jsonl 2> gpurun_out/r02e_configs_profile_n8.err; python tools/show_profile.py gpurun_out/r02e_configs_profile_n8.jsonl; tail -3 gpurun_out/r02e_configs_profile_n8.err
+# 4. the multi-rank suite (every backend through the plan API; 8 ranks)
+timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -x -q -k all_backends 2>&1 | tee gpurun_out/r02e_pytest_n8.log | tail -8
+# 5. host link ceiling at 8 GPUs (what bounds e2e), process-grid search on real GPUs
+timeout 200 $TR --master-port 29703 tools/e2e_probe.py > gpurun_out/r02e_e2e_probe_n8.jsonl 2> gpurun_out/r02e_e2e_probe_n8.err; cut -c 1-260 gpurun_out/r02e_e2e_probe_n8.jsonl
+DTFFTB_LOG=1 timeout 300 $TR --master-port 29704 tools/grid_search_probe.py > gpurun_out/r02e_grid_search_n8.txt 2>&1; grep -v "OMP_NUM\|^\*\*\*" gpurun_out/r02e_grid_search_n8.txt | tail -12
