@@ -425,6 +425,70 @@ DmaBlock dma_block(const Box& b, bool transposing, long long staging_off) {
     return d;
 }
 
+namespace {
+// overlap of the two pencils along global axis A
+void overlap_along(const RankLayout& a, const RankLayout& b, int A, long long* lo, long long* hi) {
+    long long l = 0, h = 1ll << 40;
+    for (int j = 0; j < a.ndims; ++j)
+        if (a.axis[j] == A) l = std::max<long long>(l, a.starts[j]), h = std::min<long long>(h, (long long)a.starts[j] + a.counts[j]);
+    for (int j = 0; j < b.ndims; ++j)
+        if (b.axis[j] == A) l = std::max<long long>(l, b.starts[j]), h = std::min<long long>(h, (long long)b.starts[j] + b.counts[j]);
+    *lo = l, *hi = std::max(l, h);
+}
+}  // namespace
+
+int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage) {
+    const RankLayout src = layout_of(sender_src), dst = layout_of(receiver_dst);
+    bool tr = false;
+    const Box b = intersect_box(src, dst, &tr);
+    if (b.empty()) return 1;
+    long long target = 16ll << 20;
+    if (const char* e = getenv("DTFFTB_DMA_SUB_BYTES")) target = std::max(1ll, atoll(e));
+    long long lo = 0, hi = 0;
+    overlap_along(src, dst, src.axis[src.ndims - 1], &lo, &hi);
+    long long n = (b.volume() * base_storage) / target;
+    n = std::min<long long>(n, (hi - lo) / 32);
+    return (int)std::max<long long>(1, std::min<long long>(8, n));
+}
+
+void dma_sub_range(const Pencil& sender_src, const Pencil& receiver_dst, int s, int nsub, int* axis, long long* lo,
+                   long long* hi) {
+    const RankLayout src = layout_of(sender_src), dst = layout_of(receiver_dst);
+    const int A = src.axis[src.ndims - 1];
+    long long l = 0, h = 0;
+    overlap_along(src, dst, A, &l, &h);
+    *axis = A;
+    *lo = l + (h - l) * s / nsub;
+    *hi = l + (h - l) * (s + 1) / nsub;
+}
+
+Box block_box(const Pencil& sender_src, const Pencil& receiver_dst, int s, int nsub, bool* transposing) {
+    const RankLayout src = layout_of(sender_src), dst = layout_of(receiver_dst);
+    if (nsub <= 1) return intersect_box(src, dst, transposing);
+    long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
+    int A = 0;
+    dma_sub_range(sender_src, receiver_dst, s, nsub, &A, &clip[0][0], &clip[0][1]);
+    if (A != 0) {
+        clip[A][0] = clip[0][0], clip[A][1] = clip[0][1];
+        clip[0][0] = 0, clip[0][1] = 1ll << 40;
+    }
+    return intersect_box_clipped(src, dst, clip, transposing);
+}
+
+Box local_box_for_block(const Pencil& send, const Pencil& recv, const Pencil& x_src, const Pencil& x_dst, int s, int nsub) {
+    const RankLayout src = layout_of(send), dst = layout_of(recv), xs = layout_of(x_src), xd = layout_of(x_dst);
+    long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
+    for (int A = 0; A < src.ndims; ++A) overlap_along(xs, xd, A, &clip[A][0], &clip[A][1]);  // the block's global box
+    if (nsub > 1) {
+        int A = 0;
+        long long lo = 0, hi = 0;
+        dma_sub_range(x_src, x_dst, s, nsub, &A, &lo, &hi);
+        clip[A][0] = lo, clip[A][1] = hi;
+    }
+    bool tr = false;
+    return intersect_box_clipped(src, dst, clip, &tr);
+}
+
 Box local_box_for_peer(const Pencil& send, const Pencil& recv, const Pencil& next_of_peer) {
     const RankLayout src = layout_of(send), dst = layout_of(recv), nxt = layout_of(next_of_peer);
     long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};

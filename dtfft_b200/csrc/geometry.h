@@ -156,11 +156,27 @@ struct DmaBlock {
 };
 DmaBlock dma_block(const Box& b, bool transposing, long long staging_off);
 
+// A peer block is cut into `nsub` slices along the SLOWEST axis of the sender's source pencil so that the pack of
+// slice s + 1 runs beside the copy of slice s (with few peers a whole block would serialise pack and copy).
+// Sender and receiver derive the same count from what both know: the block's bytes and its extent along that axis
+// (a slice keeps at least 32 elements of it, a full tile width wherever that axis is somebody's fastest one).
+// DTFFTB_DMA_SUB_BYTES (default 16 MiB) is the slice size aimed at; at most 8 slices.
+int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage);
+// Global index range [lo, hi) of slice s of n of the block (sender_src -> receiver_dst) along that axis (*axis).
+void dma_sub_range(const Pencil& sender_src, const Pencil& receiver_dst, int s, int nsub, int* axis, long long* lo,
+                   long long* hi);
+// The block (or its slice) as a direct-store box: intersect_box clipped to the slice.
+Box block_box(const Pencil& sender_src, const Pencil& receiver_dst, int s, int nsub, bool* transposing);
+
 // The part of a LOCAL transposition `send -> recv` (one rank in its communicator) that writes exactly what
 // member `peer` of the exchanging transposition `recv -> next_by_member[...]` will be sent: the global-index
 // range of `next_by_member[peer]` clipped out of the local transposition.  Lets the local transposition run
 // peer by peer in front of the packs of a DMA-mode exchange (Plan::run_transpose_pair).
 Box local_box_for_peer(const Pencil& send, const Pencil& recv, const Pencil& next_of_peer);
+// Same, restricted to slice s of n of the block (x_src -> x_dst) of the exchange: with side 0 the exchange follows
+// (x_src = my pencil after the local transposition, x_dst = the peer's destination), with side 1 it precedes
+// (x_src = the sender's source, x_dst = my pencil before the local transposition).
+Box local_box_for_block(const Pencil& send, const Pencil& recv, const Pencil& x_src, const Pencil& x_dst, int s, int nsub);
 
 // ---- brick <-> pencil reshape over NCCL: pack -> all-to-all(v) -> unpack -------------------
 // Block (me -> i) is the global-index intersection of my source with i's destination, carried

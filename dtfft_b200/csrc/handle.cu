@@ -16,7 +16,7 @@ void ReshapeHandle::destroy() {
     peer_pieces_[1].clear();
     dma_pack_.reset();
     dma_self_.reset();
-    dma_blocks_.clear();
+    dma_subs_.clear();
     dma_ = false;
     dma_bases_ = nullptr;
     for (int i = 0; i < 2; ++i) {
@@ -108,14 +108,18 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
             bool all_ok = true;
             long long max_block_bytes = 0;
             for (int r = 0; r < P && all_ok; ++r) {
-                const RankLayout sr = layout_of(send_by_member[(size_t)r]);
                 for (int i = 0; i < P && all_ok; ++i) {
                     if (i == r) continue;
-                    bool tr = false;
-                    const Box b = intersect_box(sr, layout_of(recv_by_member[(size_t)i]), &tr);
-                    if (b.empty()) continue;
-                    all_ok = dma_block(b, tr, 0).ok;
-                    max_block_bytes = std::max(max_block_bytes, b.volume() * es_);
+                    const int nsub = dma_nsub(send_by_member[(size_t)r], recv_by_member[(size_t)i], es_);
+                    long long bytes = 0;
+                    for (int q = 0; q < nsub && all_ok; ++q) {
+                        bool tr = false;
+                        const Box b = block_box(send_by_member[(size_t)r], recv_by_member[(size_t)i], q, nsub, &tr);
+                        if (b.empty()) continue;
+                        all_ok = dma_block(b, tr, 0).ok;
+                        bytes += b.volume() * es_;
+                    }
+                    max_block_bytes = std::max(max_block_bytes, bytes);
                 }
             }
             const char* e = getenv("DTFFTB_FUSED_MODE");
@@ -124,22 +128,31 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
             // a copy costs a few microseconds of set-up: below ~1 MiB per peer the single direct-store kernel wins
             dma_ = all_ok && !force_store && (force_dma || max_block_bytes >= (1ll << 20));
             if (dma_) {
-                dma_blocks_.assign((size_t)P, DmaBlock{});
-                std::vector<Box> packs((size_t)P), selfs((size_t)P);
+                dma_subs_.assign((size_t)P, std::vector<DmaSub>());
+                std::vector<Box> packs, selfs((size_t)P);
+                selfs[(size_t)me] = fused_boxes_[(size_t)me];
                 long long off = 0;
                 for (int i = 0; i < P; ++i) {
-                    if (i == me || fused_boxes_[(size_t)i].empty()) {
-                        if (i == me) selfs[(size_t)i] = fused_boxes_[(size_t)i];
-                        dma_blocks_[(size_t)i].ok = true;
-                        continue;
+                    if (i == me) continue;
+                    const int nsub = dma_nsub(send, recv_by_member[(size_t)i], es_);
+                    for (int q = 0; q < nsub; ++q) {
+                        bool tr = false;
+                        const Box b = block_box(send, recv_by_member[(size_t)i], q, nsub, &tr);
+                        DmaSub sub;
+                        if (!b.empty()) {
+                            sub.blk = dma_block(b, tr, off);
+                            sub.pack_index = (int)packs.size();
+                            packs.push_back(sub.blk.pack);
+                            off += b.volume();
+                        }
+                        dma_subs_[(size_t)i].push_back(sub);
                     }
-                    dma_blocks_[(size_t)i] = dma_block(fused_boxes_[(size_t)i], fused_family_ == FAM_T, off);
-                    packs[(size_t)i] = dma_blocks_[(size_t)i].pack;
-                    off += fused_boxes_[(size_t)i].volume();
                 }
                 dma_pack_.reset(new Kernel);
-                rc = dma_pack_->create_boxes(fused_family_, es_, packs);
-                if (rc) return rc;
+                if (!packs.empty()) {
+                    rc = dma_pack_->create_boxes(fused_family_, es_, packs);
+                    if (rc) return rc;
+                }
                 dma_self_.reset(new Kernel);
                 rc = dma_self_->create_boxes(fused_family_, es_, selfs);
                 if (rc) return rc;
@@ -265,7 +278,9 @@ int ReshapeHandle::ensure_dma_resources() {
             if (ce != cudaSuccess) return cuda_error(ce);
         }
     }
-    while (pack_done_.size() < members_.size()) {
+    size_t n_packs = 0;
+    for (auto& v : dma_subs_) n_packs += v.size();
+    while (pack_done_.size() < n_packs) {
         cudaEvent_t e;
         ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
         if (ce != cudaSuccess) return cuda_error(ce);
@@ -283,24 +298,27 @@ int ReshapeHandle::dma_begin(void* out, cudaStream_t stream) {
     if (rc) return rc;
     dma_bases_ = &maps_.find(out)->second.bases;
     copy_used_[0] = copy_used_[1] = false;
-    copy_turn_ = 0;
     return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1), stream);  // every member's `out` is free
 }
 
-int ReshapeHandle::dma_send(const void* in, void* out, void* aux, int peer, cudaStream_t stream) {
+int ReshapeHandle::dma_send(const void* in, void* out, void* aux, int peer, int sub, cudaStream_t stream) {
     (void)out;
     if (!dma_mode() || !dma_bases_ || peer < 0 || peer >= (int)members_.size() || peer == me_) return DTFFTB_ERROR_INTERNAL;
+    if (sub < 0 || sub >= (int)dma_subs_[(size_t)peer].size()) return DTFFTB_ERROR_INTERNAL;
     if (!aux) return DTFFT_ERROR_INVALID_AUX;
-    const DmaBlock& d = dma_blocks_[(size_t)peer];
-    if (d.run <= 0 || fused_boxes_[(size_t)peer].empty()) return DTFFT_SUCCESS;
-    int rc = dma_pack_->execute(in, aux, stream, peer + 1, false);  // block -> staging, in destination row order
+    const DmaSub& ds = dma_subs_[(size_t)peer][(size_t)sub];
+    const DmaBlock& d = ds.blk;
+    if (ds.pack_index < 0 || d.run <= 0) return DTFFT_SUCCESS;
+    int rc = dma_pack_->execute(in, aux, stream, ds.pack_index + 1, false);  // slice -> staging, in destination row order
     if (rc) return rc;
-    cudaError_t ce = cudaEventRecord(pack_done_[(size_t)peer], stream);
+    const size_t ev = (size_t)ds.pack_index;
+    cudaError_t ce = cudaEventRecord(pack_done_[ev], stream);
     if (ce != cudaSuccess) return cuda_error(ce);
-    const int c = copy_turn_++ & 1;
+    // the slices of one peer travel in order on ONE copy stream (its pairwise flag counts them); peers alternate
+    const int c = copy_stream_of(peer);
     cudaStream_t cs = copy_streams_[c];
     copy_used_[c] = true;
-    ce = cudaStreamWaitEvent(cs, pack_done_[(size_t)peer], 0);
+    ce = cudaStreamWaitEvent(cs, pack_done_[ev], 0);
     if (ce != cudaSuccess) return cuda_error(ce);
     cudaMemcpy3DParms p{};
     const size_t row_bytes = (size_t)(d.run * es_);
@@ -318,17 +336,15 @@ int ReshapeHandle::dma_self(const void* in, void* out, cudaStream_t stream) {
     return dma_self_->execute_all(in, out, stream);
 }
 
-// Tell `peer` that my block has landed in its array: enqueued on the copy stream that carried it.
-int ReshapeHandle::dma_signal(int peer) {
+// Tell `peer` that slice `sub` of my block has landed in its array: enqueued on the copy stream that carried it.
+int ReshapeHandle::dma_signal(int peer, int sub) {
     if (!dma_mode() || peer < 0 || peer >= (int)members_.size() || peer == me_) return DTFFTB_ERROR_INTERNAL;
-    // the copy of `peer` was the last one enqueued on its stream
-    const int c = (copy_turn_ - 1) & 1;
-    return ctx_.peers->signal(members_, 6 + (comm_id_ - 1), peer, copy_streams_[c]);
+    return ctx_.peers->signal(members_, 6 + (comm_id_ - 1), peer, sub, copy_streams_[copy_stream_of(peer)]);
 }
 
-int ReshapeHandle::dma_wait(int source, cudaStream_t stream) {
+int ReshapeHandle::dma_wait(int source, int sub, cudaStream_t stream) {
     if (!dma_mode() || source < 0 || source >= (int)members_.size() || source == me_) return DTFFTB_ERROR_INTERNAL;
-    return ctx_.peers->wait(members_, 6 + (comm_id_ - 1), source, stream);
+    return ctx_.peers->wait(members_, 6 + (comm_id_ - 1), source, sub, stream);
 }
 
 int ReshapeHandle::dma_end(cudaStream_t stream, bool landed_barrier) {
@@ -350,25 +366,28 @@ int ReshapeHandle::execute_dma(void* in, void* out, cudaStream_t stream, void* a
     int rc = dma_begin(out, stream);
     if (rc) return rc;
     for (int k = 1; k < P; ++k) {  // rotated order: at any time every member receives from one peer
-        rc = dma_send(in, out, aux, (me_ + k) % P, stream);
-        if (rc) return rc;
+        const int p = (me_ + k) % P;
+        for (int q = 0; q < n_subs_to(p); ++q) {
+            rc = dma_send(in, out, aux, p, q, stream);
+            if (rc) return rc;
+        }
     }
     rc = dma_self(in, out, stream);  // local HBM work beside the copies
     if (rc) return rc;
     return dma_end(stream, true);
 }
 
-int ReshapeHandle::local_piece(const void* in, void* out, int side, int peer, const std::vector<Pencil>& other_by_member,
-                               cudaStream_t stream) {
-    if (!is_local_transpose() || (side != 0 && side != 1) || peer < 0 || peer >= (int)other_by_member.size())
-        return DTFFTB_ERROR_INTERNAL;
-    auto it = peer_pieces_[side].find(peer);
+int ReshapeHandle::local_piece(const void* in, void* out, int side, const Pencil& x_src, const Pencil& x_dst, int peer,
+                               int sub, int nsub, cudaStream_t stream) {
+    if (!is_local_transpose() || (side != 0 && side != 1) || sub < 0 || sub >= nsub) return DTFFTB_ERROR_INTERNAL;
+    const std::pair<int, int> key(peer, sub);
+    auto it = peer_pieces_[side].find(key);
     if (it == peer_pieces_[side].end()) {
         std::unique_ptr<Kernel> k(new Kernel);
-        const std::vector<Box> one = {local_box_for_peer(send_, recv_by_member_[(size_t)me_], other_by_member[(size_t)peer])};
+        const std::vector<Box> one = {local_box_for_block(send_, recv_by_member_[(size_t)me_], x_src, x_dst, sub, nsub)};
         int rc = k->create_boxes(FAM_T, es_, one);
         if (rc) return rc;
-        it = peer_pieces_[side].emplace(peer, std::move(k)).first;
+        it = peer_pieces_[side].emplace(key, std::move(k)).first;
     }
     return it->second->execute_all(in, out, stream);
 }

@@ -120,17 +120,22 @@ public:
     // copy engines' 735-755 GB/s instead of the ~680 GB/s of SM stores and keeps its rate while SM kernels use
     // the HBM, so the local transposition next to it can run beside it.  The pieces, for Plan::run_transpose_pair:
     //     dma_begin(out, s)            map the members' `out`, "every member's `out` is free" barrier
-    //     dma_send(in, out, aux, p, s) pack block p (stream s), then its copy on a copy stream
+    //     dma_send(in, out, aux, p, q, s)  pack slice q of block p (stream s), then its copy on a copy stream
     //     dma_self(in, out, s)         my own block
-    //     dma_signal(p) / dma_wait(r, s)  per-pair "block has landed" flags instead of the group barrier
+    //     dma_signal(p, q) / dma_wait(r, q, s)  per-pair "slice has landed" flags instead of the group barrier
     //     dma_end(s, barrier)          join the copy streams (+ "all landed" barrier)
     bool dma_mode() const { return created_ && has_exchange_ && backend_ == BACKEND_NVLINK_FUSED && dma_; }
     int dma_begin(void* out, cudaStream_t stream);
-    int dma_send(const void* in, void* out, void* aux, int peer, cudaStream_t stream);
+    int dma_send(const void* in, void* out, void* aux, int peer, int sub, cudaStream_t stream);
+    // slices of the block I send to member `peer` / receive from member `source` (geometry.h: dma_nsub)
+    int n_subs_to(int peer) const { return peer == me_ ? 1 : (int)dma_subs_[(size_t)peer].size(); }
+    int n_subs_from(int source) const {
+        return source == me_ ? 1 : dma_nsub(send_by_member_[(size_t)source], recv_by_member_[(size_t)me_], es_);
+    }
     int dma_self(const void* in, void* out, cudaStream_t stream);
     int dma_advance_signals(cudaStream_t stream) { return ctx_.peers->advance_epoch(members_, 6 + (comm_id_ - 1), stream); }
-    int dma_signal(int peer);
-    int dma_wait(int source, cudaStream_t stream);
+    int dma_signal(int peer, int sub);
+    int dma_wait(int source, int sub, cudaStream_t stream);
     int dma_end(cudaStream_t stream, bool landed_barrier);
     int n_members() const { return (int)members_.size(); }
     int my_index() const { return me_; }
@@ -138,7 +143,10 @@ public:
     // Pieces of a LOCAL transposition cut by the members of the exchange next to it (geometry.h: local_box_for_peer):
     // piece `peer` writes (side 0, the exchange follows) or reads (side 1, the exchange precedes) exactly the elements
     // that travel between me and `peer` in that exchange.
-    int local_piece(const void* in, void* out, int side, int peer, const std::vector<Pencil>& other_by_member, cudaStream_t stream);
+    // (x_src -> x_dst) names the block of the exchange: side 0: my pencil after the local transposition -> the peer's
+    // destination; side 1: the sender's source -> my pencil before the local transposition; slice `sub` of `nsub`.
+    int local_piece(const void* in, void* out, int side, const Pencil& x_src, const Pencil& x_dst, int peer, int sub, int nsub,
+                    cudaStream_t stream);
 
 private:
     int execute_fused(void* in, void* out, cudaStream_t stream);
@@ -179,19 +187,23 @@ private:
     std::map<const void*, PeerMap> maps_;
     // copy-engine form
     bool dma_ = false;
-    std::vector<DmaBlock> dma_blocks_;      // per member
+    struct DmaSub {
+        DmaBlock blk;
+        int pack_index = -1;  // box of dma_pack_ (and event) of this slice; -1 = empty
+    };
+    std::vector<std::vector<DmaSub>> dma_subs_;  // [member][slice]
+    int copy_stream_of(int peer) const { return ((peer - me_ + (int)members_.size()) % (int)members_.size()) & 1; }
     std::unique_ptr<Kernel> dma_pack_;      // in -> staging, one launch per peer
     std::unique_ptr<Kernel> dma_self_;      // my own block, in -> out
     cudaStream_t copy_streams_[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> pack_done_;    // per member
+    std::vector<cudaEvent_t> pack_done_;    // per slice
     cudaEvent_t copies_done_[2] = {nullptr, nullptr};
     bool copy_used_[2] = {false, false};
-    int copy_turn_ = 0;
     const std::vector<void*>* dma_bases_ = nullptr;  // of the `out` of the exchange in flight (dma_begin)
     int execute_dma(void* in, void* out, cudaStream_t stream, void* aux);
     int ensure_dma_resources();
     // local pieces cut by the members of a neighbouring exchange: [side] keyed by member
-    std::map<int, std::unique_ptr<Kernel>> peer_pieces_[2];
+    std::map<std::pair<int, int>, std::unique_ptr<Kernel>> peer_pieces_[2];
 };
 
 }  // namespace dtfftb

@@ -152,15 +152,17 @@ __global__ void peer_barrier_kernel(uint64_t* const* __restrict__ peer_flags, ui
 __global__ void peer_epoch_kernel(uint64_t* __restrict__ epoch_counter) { *epoch_counter += 1; }
 
 // Enqueued behind the copy that carries the data: the copy has completed when this runs.
-__global__ void peer_signal_kernel(uint64_t* __restrict__ remote_flag, const uint64_t* __restrict__ epoch_counter) {
-    const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_counter);
+__global__ void peer_signal_kernel(uint64_t* __restrict__ remote_flag, const uint64_t* __restrict__ epoch_counter,
+                                   uint64_t slices, uint64_t slice) {
+    const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_counter) * slices + slice + 1;
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(epoch) : "memory");
 }
 
 __global__ void peer_wait_kernel(const uint64_t* __restrict__ my_flag, const uint64_t* __restrict__ epoch_counter,
-                                 long long timeout_cycles, uint64_t* __restrict__ err, uint64_t* __restrict__ err_host) {
-    const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_counter);
+                                 uint64_t slices, uint64_t slice, long long timeout_cycles, uint64_t* __restrict__ err,
+                                 uint64_t* __restrict__ err_host) {
+    const uint64_t epoch = *reinterpret_cast<const volatile uint64_t*>(epoch_counter) * slices + slice + 1;
     const long long t0 = clock64();
     uint64_t v;
     for (;;) {
@@ -447,28 +449,29 @@ int PeerRegistry::advance_epoch(const std::vector<int>& members, int channel, cu
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
 
-int PeerRegistry::signal(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream) {
-    if (!available_ || channel < 0 || channel >= kChannels) return DTFFTB_ERROR_INTERNAL;
+int PeerRegistry::signal(const std::vector<int>& members, int channel, int member_index, int slice, cudaStream_t stream) {
+    if (!available_ || channel < 0 || channel >= kChannels || slice < 0 || slice >= kMaxSlices) return DTFFTB_ERROR_INTERNAL;
     if (member_index < 0 || member_index >= (int)members.size()) return DTFFTB_ERROR_INTERNAL;
     int grc = 0;
     Group* g = group_for(members, channel, &grc);
     if (!g) return grc;
     const int P = world_.size();
     uint64_t* remote = (uint64_t*)peer_ptr(members[(size_t)member_index], flags_slot_, 0) + (size_t)channel * P + world_.rank();
-    peer_signal_kernel<<<1, 1, 0, stream>>>(remote, g->d_epoch);
+    peer_signal_kernel<<<1, 1, 0, stream>>>(remote, g->d_epoch, (uint64_t)kMaxSlices, (uint64_t)slice);
     cudaError_t ce = cudaGetLastError();
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }
 
-int PeerRegistry::wait(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream) {
-    if (!available_ || channel < 0 || channel >= kChannels) return DTFFTB_ERROR_INTERNAL;
+int PeerRegistry::wait(const std::vector<int>& members, int channel, int member_index, int slice, cudaStream_t stream) {
+    if (!available_ || channel < 0 || channel >= kChannels || slice < 0 || slice >= kMaxSlices) return DTFFTB_ERROR_INTERNAL;
     if (member_index < 0 || member_index >= (int)members.size()) return DTFFTB_ERROR_INTERNAL;
     int grc = 0;
     Group* g = group_for(members, channel, &grc);
     if (!g) return grc;
     const int P = world_.size();
     const uint64_t* mine = flags_ + (size_t)channel * P + members[(size_t)member_index];
-    peer_wait_kernel<<<1, 1, 0, stream>>>(mine, g->d_epoch, timeout_cycles_, flags_ + (size_t)kChannels * P, d_err_host_);
+    peer_wait_kernel<<<1, 1, 0, stream>>>(mine, g->d_epoch, (uint64_t)kMaxSlices, (uint64_t)slice, timeout_cycles_,
+                                          flags_ + (size_t)kChannels * P, d_err_host_);
     cudaError_t ce = cudaGetLastError();
     return ce == cudaSuccess ? DTFFT_SUCCESS : cuda_error(ce);
 }

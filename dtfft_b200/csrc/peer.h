@@ -64,8 +64,11 @@ public:
     // wait() spins until flag [channel][source] of mine has reached the current epoch.  Every member runs the same
     // sequence of exchanges, so the epochs agree; all three are graph-replayable like barrier().
     int advance_epoch(const std::vector<int>& members, int channel, cudaStream_t stream);
-    int signal(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream);
-    int wait(const std::vector<int>& members, int channel, int member_index, cudaStream_t stream);
+    // `slice` (0..kMaxSlices-1): the flag value is epoch * kMaxSlices + slice + 1, so the slices of one block, which
+    // land in order, need only one flag.
+    int signal(const std::vector<int>& members, int channel, int member_index, int slice, cudaStream_t stream);
+    int wait(const std::vector<int>& members, int channel, int member_index, int slice, cudaStream_t stream);
+    static constexpr int kMaxSlices = 16;
     // Collective.  Forget every barrier group and zero the flags: must be called when the 1-D
     // communicators change (process-grid search), because a new group starts at epoch 0 while the
     // flag rows of its channel may still hold the last epoch of a differently composed group.

@@ -1367,14 +1367,18 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
             return run_transpose(t2, b, c, aux);
         }
         if (rc) return rc;
+        const Pencil& mine = h2.send_by_member()[(size_t)me];  // my pencil between the two transpositions
         for (int k = 1; k < P; ++k) {
             const int p = (me + k) % P;
-            rc = h1.local_piece(a, b, 0, p, h2.recv_by_member(), stream_);
-            if (rc) return rc;
-            rc = h2.dma_send(b, c, aux, p, stream_);
-            if (rc) return rc;
+            const int nsub = h2.n_subs_to(p);
+            for (int q = 0; q < nsub; ++q) {
+                rc = h1.local_piece(a, b, 0, mine, h2.recv_by_member()[(size_t)p], p, q, nsub, stream_);
+                if (rc) return rc;
+                rc = h2.dma_send(b, c, aux, p, q, stream_);
+                if (rc) return rc;
+            }
         }
-        rc = h1.local_piece(a, b, 0, me, h2.recv_by_member(), stream_);
+        rc = h1.local_piece(a, b, 0, mine, h2.recv_by_member()[(size_t)me], me, 0, 1, stream_);
         if (rc) return rc;
         rc = h2.dma_self(b, c, stream_);
         if (rc) return rc;
@@ -1398,23 +1402,29 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
         if (rc) return rc;
         rc = h1.dma_advance_signals(stream_);  // new epoch of the pairwise "landed" flags, before any copy is enqueued
         if (rc) return rc;
+        const Pencil& mine = h1.recv_by_member()[(size_t)me];  // my pencil between the two transpositions
         for (int k = 1; k < P; ++k) {
             const int p = (me + k) % P;
-            rc = h1.dma_send(a, b, aux, p, stream_);
-            if (rc) return rc;
-            rc = h1.dma_signal(p);
-            if (rc) return rc;
+            for (int q = 0; q < h1.n_subs_to(p); ++q) {
+                rc = h1.dma_send(a, b, aux, p, q, stream_);
+                if (rc) return rc;
+                rc = h1.dma_signal(p, q);
+                if (rc) return rc;
+            }
         }
         rc = h1.dma_self(a, b, stream_);
         if (rc) return rc;
-        rc = h2.local_piece(b, c, 1, me, h1.send_by_member(), stream_);
+        rc = h2.local_piece(b, c, 1, h1.send_by_member()[(size_t)me], mine, me, 0, 1, stream_);
         if (rc) return rc;
         for (int k = 1; k < P; ++k) {  // sender (me - k) has me as its k-th target: blocks arrive in this order
             const int r = (me - k + P) % P;
-            rc = h1.dma_wait(r, stream_);
-            if (rc) return rc;
-            rc = h2.local_piece(b, c, 1, r, h1.send_by_member(), stream_);
-            if (rc) return rc;
+            const int nsub = h1.n_subs_from(r);
+            for (int q = 0; q < nsub; ++q) {
+                rc = h1.dma_wait(r, q, stream_);
+                if (rc) return rc;
+                rc = h2.local_piece(b, c, 1, h1.send_by_member()[(size_t)r], mine, r, q, nsub, stream_);
+                if (rc) return rc;
+            }
         }
         rc = h1.dma_end(stream_, false);  // my copies are done with the staging buffer; no group barrier needed
         if (rc) return rc;
@@ -1531,33 +1541,35 @@ int Plan::describe_local_piece(int t_local, int t_exchange, int side, int k, int
 
 // Introspection for host tests: the copy-engine form of one transposition on this rank (geometry.h: DmaBlock)
 // and the pieces of a local transposition cut by the members of the exchange next to it.
-int Plan::describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaBlock>* blocks, std::vector<Box>* fused) const {
+int Plan::describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaEntry>* entries) const {
     HandleSpec hs;
     int rc = handle_spec(ttype, &hs);
     if (rc) return rc;
     if (members) *members = hs.members;
     if (me) *me = hs.me;
-    blocks->clear();
-    fused->clear();
-    const RankLayout src = layout_of(hs.send[(size_t)hs.me]);
+    entries->clear();
+    const Pencil& send = hs.send[(size_t)hs.me];
     long long off = 0;
     for (size_t i = 0; i < hs.members.size(); ++i) {
-        bool tr = false;
-        const Box b = intersect_box(src, layout_of(hs.recv[i]), &tr);
-        fused->push_back(b);
-        if ((int)i == hs.me || b.empty()) {
-            DmaBlock d;
-            d.ok = true;
-            blocks->push_back(d);
-            continue;
+        const int nsub = (int)i == hs.me ? 1 : dma_nsub(send, hs.recv[i], hs.es);
+        for (int q = 0; q < nsub; ++q) {
+            DmaEntry e;
+            e.member = (int)i, e.sub = q, e.nsub = nsub;
+            bool tr = false;
+            e.fused = block_box(send, hs.recv[i], q, nsub, &tr);
+            if ((int)i == hs.me || e.fused.empty()) {
+                e.blk.ok = true;
+            } else {
+                e.blk = dma_block(e.fused, tr, off);
+                off += e.fused.volume();
+            }
+            entries->push_back(e);
         }
-        blocks->push_back(dma_block(b, tr, off));
-        off += b.volume();
     }
     return DTFFT_SUCCESS;
 }
 
-int Plan::describe_peer_piece(int t_local, int t_exchange, int side, int peer, Box* box) const {
+int Plan::describe_peer_piece(int t_local, int t_exchange, int side, int peer, int sub, int* nsub_out, Box* box) const {
     if (side != 0 && side != 1) return DTFFT_ERROR_INVALID_USAGE;
     HandleSpec hl, hx;
     int rc = handle_spec(t_local, &hl);
@@ -1566,8 +1578,14 @@ int Plan::describe_peer_piece(int t_local, int t_exchange, int side, int peer, B
     if (rc) return rc;
     if (hl.members.size() != 1) return DTFFT_ERROR_INVALID_USAGE;  // not a local transposition
     if (peer < 0 || peer >= (int)hx.members.size()) return DTFFT_ERROR_INVALID_USAGE;
-    // side 0: the exchange follows, cut by the members' DESTINATION pencils; side 1: it precedes, cut by their SOURCES
-    *box = local_box_for_peer(hl.send[0], hl.recv[0], side == 0 ? hx.recv[(size_t)peer] : hx.send[(size_t)peer]);
+    // side 0: the exchange follows: block (my pencil in between -> the peer's destination);
+    // side 1: it precedes: block (the sender's source -> my pencil in between)
+    const Pencil& x_src = side == 0 ? hx.send[(size_t)hx.me] : hx.send[(size_t)peer];
+    const Pencil& x_dst = side == 0 ? hx.recv[(size_t)peer] : hx.recv[(size_t)hx.me];
+    const int nsub = peer == hx.me ? 1 : dma_nsub(x_src, x_dst, hx.es);
+    if (nsub_out) *nsub_out = nsub;
+    if (sub < 0 || sub >= nsub) return DTFFT_ERROR_INVALID_USAGE;
+    *box = local_box_for_block(hl.send[0], hl.recv[0], x_src, x_dst, sub, nsub);
     return DTFFT_SUCCESS;
 }
 

@@ -124,8 +124,13 @@ public:
                        long long* chunk_offset) const;
     // Pieces of a LOCAL transposition pipelined with the exchange `t_exchange` next to it (geometry.h:
     // local_producer_box / local_consumer_boxes): side 0 = producer, 1 = consumer.
-    int describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaBlock>* blocks, std::vector<Box>* fused) const;
-    int describe_peer_piece(int t_local, int t_exchange, int side, int peer, Box* box) const;
+    struct DmaEntry {
+        int member = 0, sub = 0, nsub = 1;
+        DmaBlock blk;
+        Box fused;
+    };
+    int describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaEntry>* entries) const;
+    int describe_peer_piece(int t_local, int t_exchange, int side, int peer, int sub, int* nsub_out, Box* box) const;
     int describe_local_piece(int t_local, int t_exchange, int side, int k, int nchunks, std::vector<Box>* boxes) const;
     std::vector<int> transpose_types() const;
 

@@ -693,40 +693,43 @@ dtfft_error_t dtfftb_plan_describe_local_piece(dtfft_plan_t plan, int t_local, i
     return DTFFT_SUCCESS;
 }
 
-dtfft_error_t dtfftb_plan_describe_dma(dtfft_plan_t plan, int ttype, int32_t cap, int32_t* n_members, int32_t* me,
-                                       int32_t* members, int64_t* rows) {
+dtfft_error_t dtfftb_plan_describe_dma(dtfft_plan_t plan, int ttype, int32_t cap_members, int32_t cap_entries,
+                                       int32_t* n_members, int32_t* me, int32_t* members, int32_t* n_entries, int64_t* rows) {
     PLAN_OR_RETURN(plan);
-    if (!n_members) return DTFFT_ERROR_INVALID_USAGE;
+    if (!n_members || !n_entries) return DTFFT_ERROR_INVALID_USAGE;
     std::vector<int> mem;
     int my = 0;
-    std::vector<dtfftb::DmaBlock> blocks;
-    std::vector<dtfftb::Box> fused;
-    int rc = P(plan)->describe_dma(ttype, &mem, &my, &blocks, &fused);
+    std::vector<dtfftb::Plan::DmaEntry> ent;
+    int rc = P(plan)->describe_dma(ttype, &mem, &my, &ent);
     if (rc) return E(rc);
     *n_members = (int32_t)mem.size();
+    *n_entries = (int32_t)ent.size();
     if (me) *me = my;
-    if (!rows || !members || (int)mem.size() > cap) return DTFFT_SUCCESS;
-    for (size_t i = 0; i < mem.size(); ++i) {
-        members[i] = mem[i];
-        int64_t* o = rows + 27 * i;
-        const dtfftb::Box& b = blocks[i].pack;
+    if (!rows || !members || (int)mem.size() > cap_members || (int)ent.size() > cap_entries) return DTFFT_SUCCESS;
+    for (size_t i = 0; i < mem.size(); ++i) members[i] = mem[i];
+    for (size_t i = 0; i < ent.size(); ++i) {
+        int64_t* o = rows + 30 * i;
+        const dtfftb::Box& b = ent[i].blk.pack;
         o[0] = b.empty() ? 0 : b.n0, o[1] = b.n1, o[2] = b.n2, o[3] = b.in_off, o[4] = b.out_off;
         o[5] = b.is1, o[6] = b.is2, o[7] = b.os0, o[8] = b.os1, o[9] = b.os2;
-        o[10] = blocks[i].run, o[11] = blocks[i].rows, o[12] = blocks[i].planes, o[13] = blocks[i].dst_off;
-        o[14] = blocks[i].dst_pitch, o[15] = blocks[i].dst_plane_rows, o[16] = blocks[i].ok ? 1 : 0;
-        const dtfftb::Box& f = fused[i];
+        o[10] = ent[i].blk.run, o[11] = ent[i].blk.rows, o[12] = ent[i].blk.planes, o[13] = ent[i].blk.dst_off;
+        o[14] = ent[i].blk.dst_pitch, o[15] = ent[i].blk.dst_plane_rows, o[16] = ent[i].blk.ok ? 1 : 0;
+        const dtfftb::Box& f = ent[i].fused;
         o[17] = f.empty() ? 0 : f.n0, o[18] = f.n1, o[19] = f.n2, o[20] = f.in_off, o[21] = f.out_off;
         o[22] = f.is1, o[23] = f.is2, o[24] = f.os0, o[25] = f.os1, o[26] = f.os2;
+        o[27] = ent[i].member, o[28] = ent[i].sub, o[29] = ent[i].nsub;
     }
     return DTFFT_SUCCESS;
 }
 
 dtfft_error_t dtfftb_plan_describe_peer_piece(dtfft_plan_t plan, int t_local, int t_exchange, int side, int32_t peer,
-                                              int64_t* box) {
+                                              int32_t sub, int32_t* nsub, int64_t* box) {
     PLAN_OR_RETURN(plan);
     if (!box) return DTFFT_ERROR_INVALID_USAGE;
     dtfftb::Box b;
-    int rc = P(plan)->describe_peer_piece(t_local, t_exchange, side, peer, &b);
+    int ns = 1;
+    int rc = P(plan)->describe_peer_piece(t_local, t_exchange, side, peer, sub, &ns, &b);
+    if (nsub) *nsub = ns;
     if (rc) return E(rc);
     box[0] = b.empty() ? 0 : b.n0, box[1] = b.n1, box[2] = b.n2, box[3] = b.in_off, box[4] = b.out_off;
     box[5] = b.is1, box[6] = b.is2, box[7] = b.os0, box[8] = b.os1, box[9] = b.os2;

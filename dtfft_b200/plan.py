@@ -630,30 +630,34 @@ class Plan:
         return boxes
 
     def describe_dma(self, ttype) -> dict:
-        """Copy-engine form of one transposition on this rank (dtfftb_plan_describe_dma): per member the pack box,
-        the strided 3-D copy and the direct-store box of the same block."""
+        """Copy-engine form of one transposition on this rank (dtfftb_plan_describe_dma): one entry per (member, slice)
+        with the pack box, the strided 3-D copy and the direct-store box of the same slice."""
         import numpy as np
 
         L = _lib.lib()
-        n, me = C.c_int32(0), C.c_int32(0)
-        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), 0, C.byref(n), C.byref(me), None, None), "dtfftb_plan_describe_dma")
+        n, me, ne = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), 0, 0, C.byref(n), C.byref(me), None, C.byref(ne), None),
+               "dtfftb_plan_describe_dma")
         members = (C.c_int32 * n.value)()
-        rows = np.zeros((n.value, 27), np.int64)
-        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), n.value, C.byref(n), C.byref(me), members,
+        rows = np.zeros((ne.value, 30), np.int64)
+        _check(L.dtfftb_plan_describe_dma(self._h, int(ttype), n.value, ne.value, C.byref(n), C.byref(me), members, C.byref(ne),
                                           rows.ctypes.data_as(C.POINTER(C.c_int64))), "dtfftb_plan_describe_dma")
         keys = ("run", "rows", "planes", "dst_off", "dst_pitch", "dst_plane_rows", "ok")
-        return {"members": list(members), "me": me.value, "pack": rows[:, :10].copy(), "fused": rows[:, 17:].copy(),
-                "copy": [dict(zip(keys, (int(v) for v in rows[i, 10:17]))) for i in range(n.value)]}
+        entries = [{"member": int(r[27]), "sub": int(r[28]), "nsub": int(r[29]), "pack": r[:10].copy(), "fused": r[17:27].copy(),
+                    "copy": dict(zip(keys, (int(v) for v in r[10:17])))} for r in rows]
+        return {"members": list(members), "me": me.value, "entries": entries}
 
-    def describe_peer_piece(self, t_local, t_exchange, side: int, peer: int):
-        """The piece of a local transposition cut by member ``peer`` of the exchange next to it (one box)."""
+    def describe_peer_piece(self, t_local, t_exchange, side: int, peer: int, sub: int = 0):
+        """The piece of a local transposition cut by slice ``sub`` of the block exchanged with member ``peer`` of the
+        transposition next to it: (box[1, 10], slices of that block)."""
         import numpy as np
 
         box = np.zeros((1, 10), np.int64)
-        _check(_lib.lib().dtfftb_plan_describe_peer_piece(self._h, int(t_local), int(t_exchange), int(side), int(peer),
-                                                          box.ctypes.data_as(C.POINTER(C.c_int64))),
+        nsub = C.c_int32(1)
+        _check(_lib.lib().dtfftb_plan_describe_peer_piece(self._h, int(t_local), int(t_exchange), int(side), int(peer), int(sub),
+                                                          C.byref(nsub), box.ctypes.data_as(C.POINTER(C.c_int64))),
                "dtfftb_plan_describe_peer_piece")
-        return box
+        return box, nsub.value
 
     def describe_reshape(self, type_) -> dict:
         """NCCL-path geometry of one brick <-> pencil reshape on this rank (dtfftb_plan_describe_reshape)."""

@@ -417,17 +417,19 @@ dtfft_error_t dtfftb_plan_describe_chunk(dtfft_plan_t plan, int transpose_type, 
  * (one box per sender).  boxes = 10 x n int64 as fused_boxes, offsets relative to the full local arrays. */
 dtfft_error_t dtfftb_plan_describe_local_piece(dtfft_plan_t plan, int t_local, int t_exchange, int side, int32_t k,
                                                int32_t nchunks, int32_t cap, int32_t* n_boxes, int64_t* boxes);
-/* Copy-engine form of one transposition on this rank (NVLINK_FUSED, DMA mode): per member 27 int64 --
- * pack box (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2: my source -> staging, block packed in the order of its
- * destination rows), then run rows planes dst_off dst_pitch dst_plane_rows ok (one strided 3-D copy: `planes` x `rows`
- * rows of `run` elements from the dense staging block to dst_off + row * dst_pitch + plane * dst_plane_rows * dst_pitch
- * of the member's destination), then the direct-store box of the same block (10 values).  Host tests replay it. */
-dtfft_error_t dtfftb_plan_describe_dma(dtfft_plan_t plan, int ttype, int32_t cap, int32_t* n_members, int32_t* me,
-                                       int32_t* members, int64_t* rows);
-/* The piece of the LOCAL transposition t_local that writes (side 0) / reads (side 1) exactly what travels between this
- * rank and member `peer` of the exchanging transposition t_exchange next to it: one box, 10 values as above. */
+/* Copy-engine form of one transposition on this rank (NVLINK_FUSED, DMA mode): one entry of 30 int64 per (member,
+ * slice) -- pack box (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2: my source -> staging, the slice packed in the order
+ * of its destination rows), then run rows planes dst_off dst_pitch dst_plane_rows ok (one strided 3-D copy: `planes` x
+ * `rows` rows of `run` elements from the dense staging block to dst_off + row * dst_pitch + plane * dst_plane_rows *
+ * dst_pitch of the member's destination), then the direct-store box of the same slice (10 values), then member index,
+ * slice, slices of the block.  Host tests replay it. */
+dtfft_error_t dtfftb_plan_describe_dma(dtfft_plan_t plan, int ttype, int32_t cap_members, int32_t cap_entries,
+                                       int32_t* n_members, int32_t* me, int32_t* members, int32_t* n_entries, int64_t* rows);
+/* The piece of the LOCAL transposition t_local that writes (side 0) / reads (side 1) exactly slice `sub` of what travels
+ * between this rank and member `peer` of the exchanging transposition t_exchange next to it: one box, 10 values as
+ * above; *nsub = slices of that block. */
 dtfft_error_t dtfftb_plan_describe_peer_piece(dtfft_plan_t plan, int t_local, int t_exchange, int side, int32_t peer,
-                                              int64_t* box);
+                                              int32_t sub, int32_t* nsub, int64_t* box);
 
 #ifdef __cplusplus
 }

@@ -232,7 +232,7 @@ def main():
     experimental = os.environ.get("DTFFTB_TEST_EXPERIMENTAL", "0") == "1"
     if experimental and Backend.NVLINK_FUSED in backends:
         os.environ["DTFFTB_TRANSPOSE_OVERLAP"] = "3"
-        dims = [40, 36, 32 * world + 1]
+        dims = [96, 36, 32 * world + 1]  # x = 96: the copy-engine form cuts the blocks into up to 3 slices
         plan = PlanC2C(dims, comm=comm, config=Config(backend=Backend.NVLINK_FUSED, enable_z_slab=False))
         os.environ.pop("DTFFTB_TRANSPOSE_OVERLAP")
         assert plan.grid_dims == [1, 1, world], plan.grid_dims

@@ -41,4 +41,5 @@ def test_fused_backend_copy_engine_form_multi_gpu(cuda):
     """NVLINK_FUSED with every exchange in its copy-engine form (pack -> one strided 3-D copy per peer; the
     automatic rule keeps the direct-store kernel below 1 MiB per peer, i.e. for every test-sized case) and the
     peer-by-peer pipelines of Plan::run_transpose_pair."""
-    run_worker(cuda, {"DTFFTB_FUSED_MODE": "dma", "DTFFTB_TEST_BACKENDS": "NVLINK_FUSED", "DTFFTB_TEST_EXPERIMENTAL": "1"})
+    run_worker(cuda, {"DTFFTB_FUSED_MODE": "dma", "DTFFTB_TEST_BACKENDS": "NVLINK_FUSED", "DTFFTB_TEST_EXPERIMENTAL": "1",
+                      "DTFFTB_DMA_SUB_BYTES": "4096"})  # blocks cut into slices even at test sizes

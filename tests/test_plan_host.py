@@ -6,6 +6,7 @@ Ground truth for every exchange is what the reference's host MPI-datatype path d
 (src/dtfft_reshape_handle_datatype.F90:436-847) = slicing a global array; the product's fused
 boxes are replayed in numpy (oracle.pipeline.apply_boxes) and must reproduce it bit for bit.
 """
+import os
 import numpy as np
 import pytest
 
@@ -628,18 +629,35 @@ def _dma_copy(staging, dst, cp, pack_off):
             dst[d0: d0 + run] = staging[s0: s0 + run]
 
 
+@pytest.fixture(params=[None, "2048"], ids=["whole-blocks", "sliced"])
+def sub_bytes(request):
+    """DTFFTB_DMA_SUB_BYTES: None = default (16 MiB: test-sized blocks travel whole), 2048 = blocks cut into slices."""
+    old = os.environ.get("DTFFTB_DMA_SUB_BYTES")
+    if request.param is None:
+        os.environ.pop("DTFFTB_DMA_SUB_BYTES", None)
+    else:
+        os.environ["DTFFTB_DMA_SUB_BYTES"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("DTFFTB_DMA_SUB_BYTES", None)
+    else:
+        os.environ["DTFFTB_DMA_SUB_BYTES"] = old
+
+
 @pytest.mark.parametrize("dims,grid", [((24, 20, 36), [1, 1, 4]), ((17, 13, 29), [1, 1, 3]), ((16, 12, 10), [1, 2, 2]),
-                                       ((33, 9, 14), [1, 3, 2]), ((40, 36), [1, 4]), ((21, 10), [1, 3])])
-def test_dma_blocks_deliver_every_transposition(dims, grid):
-    """Every transposition as pack -> one strided 3-D copy per peer (+ the self block stored directly): the members'
-    destinations must equal the datatype truth, every element written exactly once, and the staging blocks must tile
-    the workspace the handle asks for."""
+                                       ((33, 9, 14), [1, 3, 2]), ((40, 36), [1, 4]), ((21, 10), [1, 3]),
+                                       ((96, 80, 72), [1, 1, 2])])
+def test_dma_blocks_deliver_every_transposition(dims, grid, sub_bytes):
+    """Every transposition as pack -> one strided 3-D copy per (peer, slice) (+ the self block stored directly): the
+    members' destinations must equal the datatype truth, every element written exactly once, and the staging slices
+    must tile the workspace the handle asks for."""
     nranks = int(np.prod(grid))
     cfg = Config(enable_z_slab=False)
     plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True), cart_dims=grid)
     comm_dims = plans[0].grid_dims
     G = P.global_array(dims, np.complex128, kind="index")
     SENT = np.complex128(-7 - 7j)
+    sliced = 0
     for t in ([1, -1] if len(dims) == 2 else [1, -1, 2, -2]):
         src = P.scatter_input(G, list(dims), comm_dims, t)
         want = P.transpose_datatype(G, list(dims), comm_dims, t)
@@ -649,23 +667,24 @@ def test_dma_blocks_deliver_every_transposition(dims, grid):
             d = plan.describe_dma(t)
             members, me = d["members"], d["me"]
             assert members[me] == r
-            remote = sum(int(np.prod(d["fused"][i][:3])) for i in range(len(members)) if i != me and d["fused"][i][0] > 0)
+            remote = sum(int(np.prod(e["fused"][:3])) for e in d["entries"] if e["member"] != me and e["fused"][0] > 0)
             staging = np.full(max(remote, 1), SENT)
             off = 0
-            for i, peer in enumerate(members):
-                f = d["fused"][i]
+            for e in d["entries"]:
+                f, peer = e["fused"], members[e["member"]]
+                sliced += e["nsub"] > 1
                 if f[0] <= 0:
                     continue
-                if i == me:
+                if e["member"] == me:
                     P.apply_boxes(src[r], out, [f], [peer])
                     P.apply_boxes(np.ones(src[r].size, np.int32), hits, [f], [peer])
                     continue
-                cp = d["copy"][i]
-                assert cp["ok"] == 1, (t, r, i, cp)
-                assert d["pack"][i][4] == off  # blocks are packed back to back
+                cp = e["copy"]
+                assert cp["ok"] == 1, (t, r, e)
+                assert e["pack"][4] == off  # slices are packed back to back
                 vol = int(np.prod(f[:3]))
                 assert cp["run"] * cp["rows"] * cp["planes"] == vol
-                P.apply_boxes(src[r], [staging], [d["pack"][i]], [0])
+                P.apply_boxes(src[r], [staging], [e["pack"]], [0])
                 assert not np.any(staging[off: off + vol] == SENT)
                 _dma_copy(staging, out[peer], cp, off)
                 _dma_copy(np.ones(staging.size, np.int32), hits[peer], cp, off)
@@ -674,16 +693,19 @@ def test_dma_blocks_deliver_every_transposition(dims, grid):
         for r in range(nranks):
             assert np.array_equal(out[r], want[r]), (t, r)
             assert np.all(hits[r] == 1), (t, r)
+    if sub_bytes and tuple(dims) == (96, 80, 72):
+        assert sliced > 0  # the big case really was cut
     Config()._commit()
 
 
-@pytest.mark.parametrize("dims,nranks", [((24, 20, 36), 4), ((17, 13, 29), 3), ((32, 8, 16), 8), ((12, 10, 7), 2)])
-def test_peer_by_peer_pair_pipelines(dims, nranks):
+@pytest.mark.parametrize("dims,nranks", [((24, 20, 36), 4), ((17, 13, 29), 3), ((32, 8, 16), 8), ((12, 10, 7), 2),
+                                         ((96, 80, 72), 2)])
+def test_peer_by_peer_pair_pipelines(dims, nranks, sub_bytes):
     """Plan::run_transpose_pair with copy-engine exchanges on a slab-shaped grid 1 x 1 x P.  Forward: the local X->Y
-    runs in pieces cut by the members' Z pencils; after piece p the pack of block p must find exactly its source
-    elements written (the rest of the Y pencil may still hold the sentinel).  Backward: the local Y->X runs in pieces
-    cut by the senders' Z pencils; piece r may only read what sender r delivered.  All pieces together = the whole
-    transposition, every element exactly once."""
+    runs in pieces cut by the (peer, slice) blocks of the Y->Z exchange; after a piece the pack of that slice must
+    find exactly its source elements written (the rest of the Y pencil may still hold the sentinel).  Backward: the
+    local Y->X runs in pieces cut by the senders' slices; a piece may only read what that slice delivered.  All
+    pieces together = the whole transposition, every element exactly once."""
     cfg = Config(enable_z_slab=False)
     plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True), cart_dims=[1, 1, nranks])
     comm_dims = plans[0].grid_dims
@@ -697,28 +719,33 @@ def test_peer_by_peer_pair_pipelines(dims, nranks):
     for r, plan in enumerate(plans):
         d = plan.describe_dma(2)
         members, me = d["members"], d["me"]
+        by_member = {}
+        for e in d["entries"]:
+            by_member.setdefault(e["member"], []).append(e)
         mid = np.full(wantY[r].size, SENT)
         hits = np.zeros(wantY[r].size, np.int32)
-        staging = np.full(max(1, sum(int(np.prod(f[:3])) for i, f in enumerate(d["fused"]) if i != me and f[0] > 0)), SENT)
+        staging = np.full(max(1, sum(int(np.prod(e["fused"][:3])) for e in d["entries"] if e["member"] != me and e["fused"][0] > 0)), SENT)
         order = [(me + k) % len(members) for k in range(1, len(members))] + [me]
         for p in order:
-            piece = plan.describe_peer_piece(1, 2, 0, p)
-            P.apply_boxes(X[r], [mid], piece, [0])
-            P.apply_boxes(np.ones(X[r].size, np.int32), [hits], piece, [0])
-            f = d["fused"][p]
-            if f[0] <= 0:
-                continue
-            if p == me:
-                P.apply_boxes(mid, outZ, [f], [members[p]])
-            else:
-                P.apply_boxes(mid, [staging], [d["pack"][p]], [0])
-                vol, off = int(np.prod(f[:3])), int(d["pack"][p][4])
-                assert not np.any(staging[off: off + vol] == SENT), (r, p)  # the piece produced all the pack reads
-                _dma_copy(staging, outZ[members[p]], d["copy"][p], off)
+            for e in by_member[p]:
+                piece, nsub = plan.describe_peer_piece(1, 2, 0, p, e["sub"])
+                assert nsub == e["nsub"]
+                P.apply_boxes(X[r], [mid], piece, [0])
+                P.apply_boxes(np.ones(X[r].size, np.int32), [hits], piece, [0])
+                f = e["fused"]
+                if f[0] <= 0:
+                    continue
+                if p == me:
+                    P.apply_boxes(mid, outZ, [f], [members[p]])
+                else:
+                    P.apply_boxes(mid, [staging], [e["pack"]], [0])
+                    vol, off = int(np.prod(f[:3])), int(e["pack"][4])
+                    assert not np.any(staging[off: off + vol] == SENT), (r, p, e["sub"])  # the piece produced all the pack reads
+                    _dma_copy(staging, outZ[members[p]], e["copy"], off)
         assert np.array_equal(mid, wantY[r]) and np.all(hits == 1), r
     for r in range(nranks):
         assert np.array_equal(outZ[r], wantZ[r]), r
-    # ---- backward: blocks of Z -> Y land one sender at a time, the local Y -> X consumes them ------------
+    # ---- backward: slices of Z -> Y land one at a time, the local Y -> X consumes them ---------------------
     Z = P.scatter_input(G, list(dims), comm_dims, -2)
     wantX = P.transpose_datatype(G, list(dims), comm_dims, -1)
     mids = [np.full(w.size, SENT) for w in wantY]
@@ -726,34 +753,38 @@ def test_peer_by_peer_pair_pipelines(dims, nranks):
     hitsX = [np.zeros(w.size, np.int32) for w in wantX]
     descr = [plan.describe_dma(-2) for plan in plans]
     P_ = nranks
-    # self blocks first (handle.cu: dma_self precedes the waits), consumed by the piece of `me`
-    for r, plan in enumerate(plans):
+    for r, plan in enumerate(plans):  # self blocks first (handle.cu: dma_self precedes the waits)
         d = descr[r]
         me = d["me"]
-        if d["fused"][me][0] > 0:
-            P.apply_boxes(Z[r], mids, [d["fused"][me]], [d["members"][me]])
-        piece = plan.describe_peer_piece(-1, -2, 1, me)
+        for e in d["entries"]:
+            if e["member"] == me and e["fused"][0] > 0:
+                P.apply_boxes(Z[r], mids, [e["fused"]], [d["members"][me]])
+        piece, _ = plan.describe_peer_piece(-1, -2, 1, me, 0)
         P.apply_boxes(mids[r], [outX[r]], piece, [0])
         P.apply_boxes(np.ones(mids[r].size, np.int32), [hitsX[r]], piece, [0])
-    for k in range(1, P_):  # step k: every sender's k-th copy lands, then every receiver consumes that sender's piece
+    for k in range(1, P_):  # step k: every sender's block for its k-th target lands slice by slice
         for r in range(nranks):
             d = descr[r]
             me = d["me"]
             p = (me + k) % P_
-            f = d["fused"][p]
-            if f[0] <= 0:
-                continue
-            vol = int(np.prod(f[:3]))
-            staging = np.full(int(d["pack"][p][4]) + vol, SENT)
-            P.apply_boxes(Z[r], [staging], [d["pack"][p]], [0])
-            _dma_copy(staging, mids[d["members"][p]], d["copy"][p], int(d["pack"][p][4]))
-        for r, plan in enumerate(plans):
-            me = descr[r]["me"]
-            src_member = (me - k + P_) % P_
-            piece = plan.describe_peer_piece(-1, -2, 1, src_member)
-            P.apply_boxes(mids[r], [outX[r]], piece, [0])
-            P.apply_boxes(np.ones(mids[r].size, np.int32), [hitsX[r]], piece, [0])
+            ents = [e for e in d["entries"] if e["member"] == p]
+            for e in ents:
+                f = e["fused"]
+                if f[0] > 0:
+                    vol = int(np.prod(f[:3]))
+                    staging = np.full(int(e["pack"][4]) + vol, SENT)
+                    P.apply_boxes(Z[r], [staging], [e["pack"]], [0])
+                    _dma_copy(staging, mids[d["members"][p]], e["copy"], int(e["pack"][4]))
+                # ... and the receiver consumes exactly that slice right away (everything later is still the sentinel)
+                recv = d["members"][p]
+                rplan, rme = plans[recv], descr[recv]["me"]
+                src_member = (rme - k + P_) % P_
+                assert descr[recv]["members"][src_member] == r
+                piece, nsub = rplan.describe_peer_piece(-1, -2, 1, src_member, e["sub"])
+                assert nsub == e["nsub"]
+                P.apply_boxes(mids[recv], [outX[recv]], piece, [0])
+                P.apply_boxes(np.ones(mids[recv].size, np.int32), [hitsX[recv]], piece, [0])
     for r in range(nranks):
-        assert np.array_equal(outX[r], wantX[r]), r  # a piece that read ahead of its sender would have copied the sentinel
+        assert np.array_equal(outX[r], wantX[r]), r  # a piece that read ahead of its slice would have copied the sentinel
         assert np.all(hitsX[r] == 1), r
     Config()._commit()

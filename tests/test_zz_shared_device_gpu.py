@@ -28,7 +28,7 @@ def test_fused_backend_ranks_sharing_one_gpu(cuda, world, mode):
     peer-by-peer pair pipelines with pairwise landed flags)."""
     env = dict(os.environ)
     env.update({"DTFFTB_ALLOW_SHARED_DEVICE": "1", "DTFFTB_PEER_TIMEOUT_MS": "20000", "DTFFTB_TEST_EXPERIMENTAL": "1",
-                "DTFFTB_FUSED_MODE": mode, "OMP_NUM_THREADS": "1"})
+                "DTFFTB_FUSED_MODE": mode, "DTFFTB_DMA_SUB_BYTES": "4096", "OMP_NUM_THREADS": "1"})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
            os.path.join(ROOT, "tests", "_gpu_worker.py")]
