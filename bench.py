@@ -413,7 +413,12 @@ def run_ours(args):
     probe.destroy()
     tname = f"transpose_tiles_kernel<uint4,{ki['tile_a'] // 32},{ki['tile_b'] // 32},{ki['threads'] // 32}>"
     kernel_name = f"{tname} (one launch per local transposition)"
-    if R["backend"] == "NVLINK_FUSED":
+    forms = {t.name: plan.exchange_form(t) for t, _, _ in order}
+    if R["backend"] == "NVLINK_FUSED" and any(v["form"] == "copy engines" for v in forms.values()):
+        ncop = max(v["copies_per_execute"] for v in forms.values())
+        exchange_kernel_name = (f"{tname} packing each peer slice locally + {ncop} strided cudaMemcpy3DAsync copies to the "
+                                "peers' final addresses (+ peer barriers / pairwise flags)")
+    elif R["backend"] == "NVLINK_FUSED":
         exchange_kernel_name = f"{tname} with peer-mapped destinations (+ peer barriers)"
     else:
         exchange_kernel_name = "transpose_tiles_kernel (pack) + ncclSend/Recv + rows_copy_kernel (unpack)"
@@ -535,7 +540,7 @@ def run_ours(args):
         "dtype": "c128 (opaque 16-byte moves)", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(world=world),
                    "global_dims": dims, "grid": grid, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
-                   "backend": R["backend"], "transposition_ms": per_type,
+                   "backend": R["backend"], "transposition_ms": per_type, "exchange_form": forms,
                    "switches": {k: os.environ[k] for k in ("DTFFTB_TRANSPOSE_OVERLAP", "DTFFTB_FUSED_MODE",
                                                             "DTFFTB_GRAPHS", "DTFFTB_TILE") if k in os.environ},
                    "backends_ms_per_step": {k: v["ms"] for k, v in results.items()},

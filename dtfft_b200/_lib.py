@@ -135,6 +135,7 @@ def _declare_plan_api(L):
         "dtfftb_plan_get_stats": [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "dtfftb_plan_peer_error": [vp],
         "dtfftb_plan_get_fallbacks": [vp, C.POINTER(C.c_int64)],
+        "dtfftb_plan_get_exchange_form": [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "dtfftb_plan_set_overlap": [vp, C.c_int, C.c_int],
         "dtfftb_plan_set_graphs": [vp, C.c_int],
         "dtfftb_plan_get_overlap": [vp, C.POINTER(C.c_int)],

@@ -1387,7 +1387,9 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
         stat_launches_ += 2 + 3 * P;
         stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
         stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
-        stat_overlapped_ += 1;
+        // replayed from a CUDA graph this pipeline loses part of its overlap (2 B200: 2.06 vs 1.91 ms per cycle,
+        // profiles/r02f_bench_n2_dma*.json), like the FFT stage overlap did: it stays eager
+        stat_overlapped_ += 1, stat_eager_only_ += 1;
         return DTFFT_SUCCESS;
     }
     if (pair_overlap_ && distinct && aux && h1.dma_mode() && h2.is_local_transpose() && h1.min_member_slow_extent() > 0) {
@@ -1431,7 +1433,9 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
         stat_launches_ += 1 + 5 * P;
         stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
         stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
-        stat_overlapped_ += 1;
+        // replayed from a CUDA graph this pipeline loses part of its overlap (2 B200: 2.06 vs 1.91 ms per cycle,
+        // profiles/r02f_bench_n2_dma*.json), like the FFT stage overlap did: it stays eager
+        stat_overlapped_ += 1, stat_eager_only_ += 1;
         return DTFFT_SUCCESS;
     }
     long long nch = transpose_overlap_;

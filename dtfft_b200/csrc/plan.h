@@ -102,6 +102,23 @@ public:
     }
     int64_t graph_replays() const { return stat_graph_replays_; }
     int64_t fallbacks() const { return stat_fallbacks_; }
+    // How one transposition moves its data: 0 local kernel only, 1 NCCL, 2 direct-store kernel, 3 copy engines
+    // (*n_slices = copies this rank issues per execute).
+    int exchange_form(int ttype, int* form, int* n_slices) const {
+        auto it = handles_.find(ttype);
+        if (it == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
+        const ReshapeHandle& h = *it->second;
+        *n_slices = 0;
+        if (!h.has_exchange()) *form = 0;
+        else if (h.backend() != BACKEND_NVLINK_FUSED) *form = 1;
+        else if (!h.dma_mode()) *form = 2;
+        else {
+            *form = 3;
+            for (int i = 0; i < h.n_members(); ++i)
+                if (i != h.my_index()) *n_slices += h.n_subs_to(i);
+        }
+        return DTFFT_SUCCESS;
+    }
     int overlap_chunks() const { return overlap_chunks_; }
     int64_t overlapped_stages() const { return stat_overlapped_; }
 

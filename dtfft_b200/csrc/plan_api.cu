@@ -516,6 +516,15 @@ dtfft_error_t dtfftb_plan_get_stats(dtfft_plan_t plan, int64_t* kernel_launches,
     if (remote_bytes) *remote_bytes = c;
     return DTFFT_SUCCESS;
 }
+dtfft_error_t dtfftb_plan_get_exchange_form(dtfft_plan_t plan, int transpose_type, int* form, int* n_slices) {
+    PLAN_OR_RETURN(plan);
+    int f = 0, n = 0;
+    int rc = P(plan)->exchange_form(transpose_type, &f, &n);
+    if (rc) return E(rc);
+    if (form) *form = f;
+    if (n_slices) *n_slices = n;
+    return DTFFT_SUCCESS;
+}
 dtfft_error_t dtfftb_plan_set_overlap(dtfft_plan_t plan, int nchunks, int exchange_ctas) {
     PLAN_OR_RETURN(plan);
     P(plan)->set_overlap(nchunks < 1 ? 1 : nchunks, exchange_ctas < 0 ? 0 : exchange_ctas);

@@ -556,6 +556,14 @@ class Plan:
         """CUDA-graph replay of execute (extension, see dtfftb_plan_set_graphs)."""
         _check(_lib.lib().dtfftb_plan_set_graphs(self._h, int(bool(enable))), "dtfftb_plan_set_graphs")
 
+    def exchange_form(self, transpose_type) -> dict:
+        """How one transposition moves its data on this rank (dtfftb_plan_get_exchange_form)."""
+        f, n = C.c_int(0), C.c_int(0)
+        _check(_lib.lib().dtfftb_plan_get_exchange_form(self._h, int(transpose_type), C.byref(f), C.byref(n)),
+               "dtfftb_plan_get_exchange_form")
+        names = {0: "local kernel", 1: "nccl", 2: "direct-store kernel", 3: "copy engines"}
+        return {"form": names.get(f.value, str(f.value)), "copies_per_execute": n.value}
+
     @property
     def fallbacks(self) -> int:
         """NVLINK_FUSED: transpositions / reshapes that ran on the NCCL stand-in (buffer not shareable over cudaIpc)."""

@@ -8,7 +8,8 @@ timeout 400 $TR --master-port 29700 bench.py --gpus 8 > gpurun_out/r02e_bench_n8
 run() { name=$1; shift; env "$@" timeout 300 $TR --master-port 29701 bench.py --gpus 8 --backend nvlink > gpurun_out/r02e_bench_n8_$name.json 2> gpurun_out/r02e_bench_n8_$name.err; python tools/show_bench.py gpurun_out/r02e_bench_n8_$name.json 2>&1 | head -4; tail -2 gpurun_out/r02e_bench_n8_$name.err; }
 run store DTFFTB_FUSED_MODE=store
 run dma_nopair DTFFTB_FUSED_MODE=dma DTFFTB_PAIR_OVERLAP=0
-run dma_nograph DTFFTB_FUSED_MODE=dma DTFFTB_GRAPHS=0
+run dma_nosub DTFFTB_FUSED_MODE=dma DTFFTB_DMA_SUB_BYTES=100000000000
+run dma_sub8m DTFFTB_FUSED_MODE=dma DTFFTB_DMA_SUB_BYTES=8388608
 # 3. configs C3 / C4 / C5 at full size, per stage against the roofline
 timeout 600 $TR --master-port 29702 tools/configs_profile.py --configs c3,c4,c5 --backends nvlink,nccl > gpurun_out/r02e_configs_profile_n8.jsonl 2> gpurun_out/r02e_configs_profile_n8.err; python tools/show_profile.py gpurun_out/r02e_configs_profile_n8.jsonl; tail -3 gpurun_out/r02e_configs_profile_n8.err
 # 4. the multi-rank suite (every backend through the plan API; 8 ranks)
