@@ -541,7 +541,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD.format(world=world),
                    "global_dims": dims, "grid": grid, "element_bytes": ES, "bytes_per_step": CYCLE_BYTES,
                    "backend": R["backend"], "transposition_ms": per_type, "exchange_form": forms,
-                   "switches": {k: os.environ[k] for k in ("DTFFTB_TRANSPOSE_OVERLAP", "DTFFTB_FUSED_MODE",
+                   "switches": {k: os.environ[k] for k in ("DTFFTB_PAIR_OVERLAP", "DTFFTB_FUSED_MODE", "DTFFTB_DMA_SUB_BYTES",
                                                             "DTFFTB_GRAPHS", "DTFFTB_TILE") if k in os.environ},
                    "backends_ms_per_step": {k: v["ms"] for k, v in results.items()},
                    "l2": f"working set 2 x {n_local * ES / 2**20:.0f} MiB per transposition per GPU >> 126 MB L2 (no flush needed)"

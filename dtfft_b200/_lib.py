@@ -148,8 +148,6 @@ def _declare_plan_api(L):
                                        C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_dma": [vp, C.c_int, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p, C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_peer_piece": [vp, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, i32p, C.POINTER(C.c_int64)],
-        "dtfftb_plan_describe_local_piece": [vp, C.c_int, C.c_int, C.c_int, C.c_int32, C.c_int32, C.c_int32, i32p,
-                                             C.POINTER(C.c_int64)],
         "dtfftb_plan_describe_reshape": [vp, C.c_int, C.c_int32, i32p, i32p, i32p, C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p],
     }

@@ -500,43 +500,6 @@ Box local_box_for_peer(const Pencil& send, const Pencil& recv, const Pencil& nex
     return intersect_box_clipped(src, dst, clip, &tr);
 }
 
-Box local_producer_box(const Pencil& send, const Pencil& recv, int k, int nchunks) {
-    const int nd = recv.ndims;
-    const RankLayout src = layout_of(send), dst = layout_of(recv);
-    const long long n = recv.counts[nd - 1];
-    const long long lo = n * k / nchunks, hi = n * (k + 1) / nchunks;
-    if (hi <= lo) return Box{};
-    long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
-    const int A = dst.axis[nd - 1];  // global axis of the destination's slowest local axis
-    clip[A][0] = recv.starts[nd - 1] + lo, clip[A][1] = recv.starts[nd - 1] + hi;
-    bool tr = false;
-    return intersect_box_clipped(src, dst, clip, &tr);
-}
-
-std::vector<Box> local_consumer_boxes(const Pencil& send, const Pencil& recv, const std::vector<Pencil>& senders_src,
-                                      int k, int nchunks) {
-    const RankLayout src = layout_of(send), dst = layout_of(recv);
-    std::vector<Box> out;
-    for (const Pencil& sp : senders_src) {
-        // what sender `sp` delivers with its chunk k: its source pencil with the slowest axis cut
-        const int nd = sp.ndims;
-        const RankLayout sl = layout_of(sp);
-        const long long n = sp.counts[nd - 1];
-        const long long lo = n * k / nchunks, hi = n * (k + 1) / nchunks;
-        if (hi <= lo) {
-            out.push_back(Box{});
-            continue;
-        }
-        long long clip[3][2] = {{0, 1ll << 40}, {0, 1ll << 40}, {0, 1ll << 40}};
-        for (int j = 0; j < nd; ++j) clip[sl.axis[j]][0] = sp.starts[j], clip[sl.axis[j]][1] = (long long)sp.starts[j] + sp.counts[j];
-        const int A = sl.axis[nd - 1];
-        clip[A][0] = sp.starts[nd - 1] + lo, clip[A][1] = sp.starts[nd - 1] + hi;
-        bool tr = false;
-        out.push_back(intersect_box_clipped(src, dst, clip, &tr));
-    }
-    return out;
-}
-
 RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankLayout& order_like) {
     const AxisView v = view_of(src, dst);
     RankLayout s;

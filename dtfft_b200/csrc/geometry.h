@@ -125,18 +125,6 @@ RankLayout slot_layout(const RankLayout& src, const RankLayout& dst, const RankL
 std::vector<Box> chunk_boxes(const Pencil& send, const std::vector<Pencil>& recv_by_member, int k, int nchunks,
                              long long* chunk_offset);
 
-// Pipelining a LOCAL transposition (1 rank in its communicator) with the exchanging one next to it
-// (transpose-only plans on slab-shaped grids: X->Y local, Y->Z exchanged, and back):
-//  * producer side: the part of the local transposition that WRITES chunk k of n of its destination
-//    pencil's slowest axis -- exactly the source range of chunk k of the exchange that follows;
-//  * consumer side: the part of the local transposition that READS what chunk k of the preceding
-//    exchange delivered: one box per sender (the sender cuts ITS source pencil along its slowest axis,
-//    chunk_boxes above), `senders_src[i]` = source pencil of member i of that exchange.
-// Offsets are relative to the full local arrays.
-Box local_producer_box(const Pencil& send, const Pencil& recv, int k, int nchunks);
-std::vector<Box> local_consumer_boxes(const Pencil& send, const Pencil& recv, const std::vector<Pencil>& senders_src,
-                                      int k, int nchunks);
-
 // ---- copy-engine form of a direct-store block (handle.h, DMA mode) ------------------------------
 // On B200 a kernel's remote stores leave as 128-byte NVLink writes and top out near 690 GB/s per direction,
 // and they collapse (to ~420 GB/s) when an HBM-bound kernel runs beside them; a copy engine moves the same

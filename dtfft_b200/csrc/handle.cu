@@ -10,8 +10,6 @@
 namespace dtfftb {
 
 void ReshapeHandle::destroy() {
-    local_pieces_[0].clear();
-    local_pieces_[1].clear();
     peer_pieces_[0].clear();
     peer_pieces_[1].clear();
     dma_pack_.reset();
@@ -453,39 +451,6 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
     long long chunk_offset = 0;  // first element of chunk k in the source pencil
     chunk_boxes(send_, recv_by_member_, k, nchunks, &chunk_offset);
     return kern.execute_all(static_cast<char*>(in) + (size_t)chunk_offset * (size_t)es_, out, stream);
-}
-
-int ReshapeHandle::local_produce(const void* in, void* out, int k, int nchunks, cudaStream_t stream) {
-    if (!is_local_transpose() || k < 0 || k >= nchunks) return DTFFTB_ERROR_INTERNAL;
-    auto it = local_pieces_[0].find(nchunks);
-    if (it == local_pieces_[0].end()) {
-        std::vector<std::unique_ptr<Kernel>> ks((size_t)nchunks);
-        for (int c = 0; c < nchunks; ++c) {
-            ks[(size_t)c].reset(new Kernel);
-            const std::vector<Box> one = {local_producer_box(send_, recv_by_member_[(size_t)me_], c, nchunks)};
-            int rc = ks[(size_t)c]->create_boxes(FAM_T, es_, one);
-            if (rc) return rc;
-        }
-        it = local_pieces_[0].emplace(nchunks, std::move(ks)).first;
-    }
-    return it->second[(size_t)k]->execute_all(in, out, stream);
-}
-
-int ReshapeHandle::local_consume(const void* in, void* out, int k, int nchunks, const std::vector<Pencil>& senders_src,
-                                 cudaStream_t stream) {
-    if (!is_local_transpose() || k < 0 || k >= nchunks) return DTFFTB_ERROR_INTERNAL;
-    auto it = local_pieces_[1].find(nchunks);
-    if (it == local_pieces_[1].end()) {
-        std::vector<std::unique_ptr<Kernel>> ks((size_t)nchunks);
-        for (int c = 0; c < nchunks; ++c) {
-            ks[(size_t)c].reset(new Kernel);
-            int rc = ks[(size_t)c]->create_boxes(FAM_T, es_, local_consumer_boxes(send_, recv_by_member_[(size_t)me_],
-                                                                                   senders_src, c, nchunks));
-            if (rc) return rc;
-        }
-        it = local_pieces_[1].emplace(nchunks, std::move(ks)).first;
-    }
-    return it->second[(size_t)k]->execute_all(in, out, stream);
 }
 
 int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {

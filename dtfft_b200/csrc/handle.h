@@ -85,18 +85,9 @@ public:
     int fused_chunk(void* in, void* out, int k, int nchunks, int max_ctas, cudaStream_t stream);
     int fused_end(cudaStream_t stream);
 
-    // ---- pipelining a LOCAL transposition with the exchange next to it (geometry.h) ---------
-    // A handle without exchange whose kernel is a tiled transpose can run in pieces: the piece that
-    // writes chunk k of its destination's slowest axis (producer of a chunked exchange), or the
-    // piece that reads what chunk k of a preceding chunked exchange delivered (consumer).
+    // A handle without exchange whose kernel is a tiled transpose can run in pieces cut by the blocks of the exchange
+    // next to it (local_piece below).
     bool is_local_transpose() const { return created_ && !has_exchange_ && is_transpose_ && send_elems_ > 0; }
-    long long dest_slow_extent() const {
-        const Pencil& r = recv_by_member_[(size_t)me_];
-        return r.ndims > 0 ? r.counts[r.ndims - 1] : 1;
-    }
-    int local_produce(const void* in, void* out, int k, int nchunks, cudaStream_t stream);
-    int local_consume(const void* in, void* out, int k, int nchunks, const std::vector<Pencil>& senders_src,
-                      cudaStream_t stream);
     const std::vector<Pencil>& send_by_member() const { return send_by_member_; }
     // Smallest slowest-axis extent of the members' source pencils, 0 if any member's source or
     // destination pencil is empty: what every member can compute alike to agree on a chunk count.
@@ -110,8 +101,6 @@ public:
         }
         return m < 0 ? 0 : m;
     }
-    // "All members' chunk has landed" between the chunks of a chunked exchange (consumer pipelining).
-    int fused_chunk_landed(cudaStream_t stream) { return fused_end(stream); }
 
     // ---- NVLINK_FUSED, copy-engine form of the exchange (geometry.h: DmaBlock) ----------------------------
     // Each peer block is packed locally in the order of its destination rows (workspace: `aux`, aux_bytes()) and
@@ -150,8 +139,6 @@ public:
 
 private:
     int execute_fused(void* in, void* out, cudaStream_t stream);
-    // piece kernels of a local transposition: [0] producer side, [1] consumer side, keyed by nchunks
-    std::map<int, std::vector<std::unique_ptr<Kernel>>> local_pieces_[2];
     std::vector<Pencil> send_by_member_;
 
     HandleContext ctx_;

@@ -61,7 +61,6 @@ int Plan::create(PlanKind kind, int ndims, const int32_t* dims, const dtfft_penc
     precision_ = precision, effort_ = effort, executor_ = executor;
     if (const char* e = getenv("DTFFTB_OVERLAP_CHUNKS")) overlap_chunks_ = std::max(1, atoi(e)), overlap_user_set_ = true;
     if (const char* e = getenv("DTFFTB_OVERLAP_CTAS")) overlap_ctas_ = std::max(0, atoi(e));
-    if (const char* e = getenv("DTFFTB_TRANSPOSE_OVERLAP")) transpose_overlap_ = std::max(1, atoi(e));
     if (const char* e = getenv("DTFFTB_PAIR_OVERLAP")) pair_overlap_ = atoi(e) != 0;
     if (const char* e = getenv("DTFFTB_GRAPHS")) graphs_enabled_ = atoi(e) != 0;
     is_transpose_plan_ = executor == DTFFT_EXECUTOR_NONE;
@@ -1302,51 +1301,12 @@ int Plan::run_fft_transpose(int dim, void* a, void* b, int sign, int ttype, void
     return DTFFT_SUCCESS;
 }
 
-int Plan::ensure_overlap_resources(long long nch, bool consumer) {
-    cudaError_t ce;
-    if (!xfer_stream_) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = greatest priority
-        ce = cudaStreamCreateWithPriority(&xfer_stream_, cudaStreamNonBlocking, hi);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaEventCreateWithFlags(&xfer_done_, cudaEventDisableTiming);
-        if (ce != cudaSuccess) return cuda_error(ce);
-    }
-    while ((long long)chunk_events_.size() < nch) {
-        cudaEvent_t e;
-        ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        chunk_events_.push_back(e);
-    }
-    if (!consumer) return DTFFT_SUCCESS;
-    if (!bar_stream_) {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        ce = cudaStreamCreateWithPriority(&bar_stream_, cudaStreamNonBlocking, hi);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaEventCreateWithFlags(&pair_start_, cudaEventDisableTiming);
-        if (ce != cudaSuccess) return cuda_error(ce);
-    }
-    while ((long long)landed_events_.size() < nch) {
-        cudaEvent_t e;
-        ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        landed_events_.push_back(e);
-    }
-    return DTFFT_SUCCESS;
-}
-
-// Two consecutive transpositions of a transpose-only schedule, a -> b -> c.  On slab-shaped process
-// grids one of them is local (one rank in its communicator, HBM-bound) and the other exchanges over
-// NVLink; with DTFFTB_TRANSPOSE_OVERLAP=n > 1 and the NVLINK_FUSED backend they are pipelined over n
-// chunks like the FFT / exchange stage overlap (run_fft_transpose):
-//   producer (local, then exchange): piece k of the local transposition writes chunk k of `b`; as soon
-//     as it is done, chunk k is stored to the peers on a second stream while piece k + 1 runs;
-//   consumer (exchange, then local): chunk k of `a` is stored to the peers; a "chunk k has landed
-//     everywhere" barrier on a third stream releases piece k of the local transposition, which reads
-//     exactly what the members' chunk k delivered, while chunk k + 1 is in flight.
-// Every member must pipeline the consumer form alike (one barrier per chunk): the chunk count is
-// derived from the members' pencils, which every rank knows.  No reference counterpart.
+// Two consecutive transpositions of a transpose-only schedule, a -> b -> c.  On slab-shaped process grids one of
+// them is local (one rank in its communicator, HBM-bound) and the other exchanges over NVLink; when the exchange
+// runs in its copy-engine form the two are pipelined peer by peer (below), otherwise they run one after the other.
+// (A chunk-wise pipeline of the direct-store kernel was measured too and dropped: the remote stores of a kernel
+// collapse to ~420 GB/s when an HBM-bound kernel runs beside them, profiles/r02c_nvlink_probe_n2.md, so it gained
+// 1.4 % at best, profiles/r02b_bench_n2_pair*.json.)  No reference counterpart.
 int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* aux) {
     auto i1 = handles_.find(t1), i2 = handles_.find(t2);
     if (i1 == handles_.end() || i2 == handles_.end()) return DTFFT_ERROR_INVALID_TRANSPOSE_TYPE;
@@ -1438,109 +1398,9 @@ int Plan::run_transpose_pair(int t1, void* a, void* b, int t2, void* c, void* au
         stat_overlapped_ += 1, stat_eager_only_ += 1;
         return DTFFT_SUCCESS;
     }
-    long long nch = transpose_overlap_;
-    int mode = 0;  // 1 = producer, 2 = consumer
-    if (nch > 1 && distinct && h1.is_local_transpose() && h2.can_chunk()) {
-        nch = std::min(nch, h2.slow_extent());
-        mode = 1;
-    } else if (nch > 1 && distinct && h1.can_chunk() && h2.is_local_transpose()) {
-        nch = std::min(nch, h1.min_member_slow_extent());  // the same number on every member
-        mode = 2;
-    }
-    if (mode == 0 || nch <= 1) {
-        int rc = run_transpose(t1, a, b, aux);
-        if (rc) return rc;
-        return run_transpose(t2, b, c, aux);
-    }
-    int rc = ensure_overlap_resources(nch, mode == 2);
+    int rc = run_transpose(t1, a, b, aux);
     if (rc) return rc;
-    cudaError_t ce;
-    int sms = 148;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const int ctas = overlap_ctas_ > 0 ? overlap_ctas_ : sms;
-    TraceRange trace(mode == 1 ? "Transpose pair (local || exchange)" : "Transpose pair (exchange || local)", kColorTranspose);
-    if (mode == 1) {
-        rc = h2.fused_begin(c, stream_);  // every member's `c` is free
-        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
-            rc = run_transpose(t1, a, b, aux);
-            if (rc) return rc;
-            return run_transpose(t2, b, c, aux);
-        }
-        if (rc) return rc;
-        for (long long k = 0; k < nch; ++k) {
-            rc = h1.local_produce(a, b, (int)k, (int)nch, stream_);
-            if (rc) return rc;
-            ce = cudaEventRecord(chunk_events_[(size_t)k], stream_);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            ce = cudaStreamWaitEvent(xfer_stream_, chunk_events_[(size_t)k], 0);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            rc = h2.fused_chunk(b, c, (int)k, (int)nch, k + 1 < nch ? ctas : 0, xfer_stream_);
-            if (rc) return rc;
-        }
-        ce = cudaEventRecord(xfer_done_, xfer_stream_);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaStreamWaitEvent(stream_, xfer_done_, 0);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        rc = h2.fused_end(stream_);  // every block has landed
-        if (rc) return rc;
-        stat_launches_ += 2 + 2 * nch;
-    } else {
-        rc = h1.fused_begin(b, stream_);  // every member's `b` is free
-        if (rc == DTFFTB_ERROR_NOT_REGISTERED) {
-            rc = run_transpose(t1, a, b, aux);
-            if (rc) return rc;
-            return run_transpose(t2, b, c, aux);
-        }
-        if (rc) return rc;
-        ce = cudaEventRecord(pair_start_, stream_);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        ce = cudaStreamWaitEvent(xfer_stream_, pair_start_, 0);
-        if (ce != cudaSuccess) return cuda_error(ce);
-        const std::vector<Pencil>& senders = h1.send_by_member();
-        for (long long k = 0; k < nch; ++k) {
-            // the last chunks have less and less to hide behind; keep the exchange narrow only while
-            // a local piece runs beside it
-            rc = h1.fused_chunk(a, b, (int)k, (int)nch, k > 0 ? ctas : 0, xfer_stream_);
-            if (rc) return rc;
-            ce = cudaEventRecord(chunk_events_[(size_t)k], xfer_stream_);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            ce = cudaStreamWaitEvent(bar_stream_, chunk_events_[(size_t)k], 0);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            rc = h1.fused_chunk_landed(bar_stream_);  // chunk k of every member has landed
-            if (rc) return rc;
-            ce = cudaEventRecord(landed_events_[(size_t)k], bar_stream_);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            ce = cudaStreamWaitEvent(stream_, landed_events_[(size_t)k], 0);
-            if (ce != cudaSuccess) return cuda_error(ce);
-            rc = h2.local_consume(b, c, (int)k, (int)nch, senders, stream_);
-            if (rc) return rc;
-        }
-        stat_launches_ += 1 + 3 * nch;
-    }
-    stat_local_ += (h1.local_elements() + h2.local_elements()) * base_storage_;
-    stat_remote_ += (h1.remote_elements() + h2.remote_elements()) * base_storage_;
-    stat_overlapped_ += 1, stat_eager_only_ += 1;
-    return DTFFT_SUCCESS;
-}
-
-int Plan::describe_local_piece(int t_local, int t_exchange, int side, int k, int nchunks, std::vector<Box>* boxes) const {
-    if (nchunks < 1 || k < 0 || k >= nchunks || (side != 0 && side != 1)) return DTFFT_ERROR_INVALID_USAGE;
-    HandleSpec hl, hx;
-    int rc = handle_spec(t_local, &hl);
-    if (rc) return rc;
-    rc = handle_spec(t_exchange, &hx);
-    if (rc) return rc;
-    if (hl.members.size() != 1) return DTFFT_ERROR_INVALID_USAGE;  // not a local transposition
-    boxes->clear();
-    if (side == 0)
-        boxes->push_back(local_producer_box(hl.send[0], hl.recv[0], k, nchunks));
-    else
-        *boxes = local_consumer_boxes(hl.send[0], hl.recv[0], hx.send, k, nchunks);
-    return DTFFT_SUCCESS;
+    return run_transpose(t2, b, c, aux);
 }
 
 // Introspection for host tests: the copy-engine form of one transposition on this rank (geometry.h: DmaBlock)
@@ -2004,15 +1864,6 @@ int Plan::destroy() {
     }
     for (cudaEvent_t e : chunk_events_) cudaEventDestroy(e);
     chunk_events_.clear();
-    if (bar_stream_) {
-        cudaStreamSynchronize(bar_stream_);
-        cudaStreamDestroy(bar_stream_);
-        bar_stream_ = nullptr;
-    }
-    for (cudaEvent_t e : landed_events_) cudaEventDestroy(e);
-    landed_events_.clear();
-    if (pair_start_) cudaEventDestroy(pair_start_);
-    pair_start_ = nullptr;
     if (xfer_done_) cudaEventDestroy(xfer_done_);
     xfer_done_ = nullptr;
     handles_.clear();

@@ -139,8 +139,8 @@ public:
     // Boxes of chunk k of n of the stage-overlapped fused transposition `ttype` (geometry.h: chunk_boxes).
     int describe_chunk(int ttype, int k, int nchunks, std::vector<int>* members, std::vector<Box>* boxes,
                        long long* chunk_offset) const;
-    // Pieces of a LOCAL transposition pipelined with the exchange `t_exchange` next to it (geometry.h:
-    // local_producer_box / local_consumer_boxes): side 0 = producer, 1 = consumer.
+    // Copy-engine form of a transposition and the pieces of the LOCAL transposition next to it, cut by the (peer,
+    // slice) blocks of that exchange (geometry.h: DmaBlock, local_box_for_block): side 0 = producer, 1 = consumer.
     struct DmaEntry {
         int member = 0, sub = 0, nsub = 1;
         DmaBlock blk;
@@ -148,7 +148,6 @@ public:
     };
     int describe_dma(int ttype, std::vector<int>* members, int* me, std::vector<DmaEntry>* entries) const;
     int describe_peer_piece(int t_local, int t_exchange, int side, int peer, int sub, int* nsub_out, Box* box) const;
-    int describe_local_piece(int t_local, int t_exchange, int side, int k, int nchunks, std::vector<Box>* boxes) const;
     std::vector<int> transpose_types() const;
 
 private:
@@ -274,9 +273,6 @@ private:
     int64_t stat_graph_replays_ = 0;
     // stage overlap
     int overlap_chunks_ = 1, overlap_ctas_ = 0;
-    // DTFFTB_TRANSPOSE_OVERLAP=n (opt-in): pipeline a local transposition with the exchanging one next to
-    // it in transpose-only schedules (Plan::run_transpose_pair)
-    int transpose_overlap_ = 1;
     // Peer-by-peer pipelining of a local transposition with a copy-engine exchange next to it (run_transpose_pair);
     // DTFFTB_PAIR_OVERLAP=0 runs the two transpositions one after the other
     bool pair_overlap_ = true;

@@ -684,24 +684,6 @@ dtfft_error_t dtfftb_plan_describe_chunk(dtfft_plan_t plan, int transpose_type, 
     return DTFFT_SUCCESS;
 }
 
-dtfft_error_t dtfftb_plan_describe_local_piece(dtfft_plan_t plan, int t_local, int t_exchange, int side, int32_t k,
-                                               int32_t nchunks, int32_t cap, int32_t* n_boxes, int64_t* boxes) {
-    PLAN_OR_RETURN(plan);
-    if (!n_boxes) return DTFFT_ERROR_INVALID_USAGE;
-    std::vector<dtfftb::Box> bx;
-    int rc = P(plan)->describe_local_piece(t_local, t_exchange, side, k, nchunks, &bx);
-    if (rc) return E(rc);
-    *n_boxes = (int32_t)bx.size();
-    if (!boxes || (int)bx.size() > cap) return DTFFT_SUCCESS;
-    for (size_t i = 0; i < bx.size(); ++i) {
-        const dtfftb::Box& b = bx[i];
-        int64_t* o = boxes + 10 * i;
-        o[0] = b.empty() ? 0 : b.n0, o[1] = b.n1, o[2] = b.n2, o[3] = b.in_off, o[4] = b.out_off;
-        o[5] = b.is1, o[6] = b.is2, o[7] = b.os0, o[8] = b.os1, o[9] = b.os2;
-    }
-    return DTFFT_SUCCESS;
-}
-
 dtfft_error_t dtfftb_plan_describe_dma(dtfft_plan_t plan, int ttype, int32_t cap_members, int32_t cap_entries,
                                        int32_t* n_members, int32_t* me, int32_t* members, int32_t* n_entries, int64_t* rows) {
     PLAN_OR_RETURN(plan);

@@ -622,21 +622,6 @@ class Plan:
                "dtfftb_plan_describe_chunk")
         return {"boxes": boxes, "chunk_offset": int(off.value)}
 
-    def describe_local_piece(self, t_local, t_exchange, side: int, k: int, nchunks: int):
-        """Boxes of piece ``k`` of a local transposition pipelined with the exchange next to it
-        (dtfftb_plan_describe_local_piece): ``side`` 0 = producer, 1 = consumer."""
-        import numpy as np
-
-        L = _lib.lib()
-        n = C.c_int32(0)
-        _check(L.dtfftb_plan_describe_local_piece(self._h, int(t_local), int(t_exchange), int(side), int(k), int(nchunks),
-                                                  0, C.byref(n), None), "dtfftb_plan_describe_local_piece")
-        boxes = np.zeros((n.value, 10), np.int64)
-        _check(L.dtfftb_plan_describe_local_piece(self._h, int(t_local), int(t_exchange), int(side), int(k), int(nchunks),
-                                                  n.value, C.byref(n), boxes.ctypes.data_as(C.POINTER(C.c_int64))),
-               "dtfftb_plan_describe_local_piece")
-        return boxes
-
     def describe_dma(self, ttype) -> dict:
         """Copy-engine form of one transposition on this rank (dtfftb_plan_describe_dma): one entry per (member, slice)
         with the pack box, the strided 3-D copy and the direct-store box of the same slice."""

@@ -414,13 +414,6 @@ dtfft_error_t dtfftb_plan_describe_reshape(dtfft_plan_t plan, int reshape_type, 
  * of the chunk in the source pencil.  Works on dry and real plans. */
 dtfft_error_t dtfftb_plan_describe_chunk(dtfft_plan_t plan, int transpose_type, int32_t k, int32_t nchunks, int32_t cap,
                                          int32_t* n_members, int64_t* boxes, int64_t* chunk_offset);
-/* Pipelining of a LOCAL transposition `t_local` (one rank in its communicator) with the exchanging
- * transposition `t_exchange` next to it in a transpose-only schedule (DTFFTB_TRANSPOSE_OVERLAP):
- * side 0 = the piece of `t_local` that writes chunk k of its destination (producer of the exchange's
- * chunk k), side 1 = the piece that reads what the members' chunk k of the preceding exchange delivered
- * (one box per sender).  boxes = 10 x n int64 as fused_boxes, offsets relative to the full local arrays. */
-dtfft_error_t dtfftb_plan_describe_local_piece(dtfft_plan_t plan, int t_local, int t_exchange, int side, int32_t k,
-                                               int32_t nchunks, int32_t cap, int32_t* n_boxes, int64_t* boxes);
 /* Copy-engine form of one transposition on this rank (NVLINK_FUSED, DMA mode): one entry of 30 int64 per (member,
  * slice) -- pack box (n0 n1 n2 in_off out_off is1 is2 os0 os1 os2: my source -> staging, the slice packed in the order
  * of its destination rows), then run rows planes dst_off dst_pitch dst_plane_rows ok (one strided 3-D copy: `planes` x

@@ -225,17 +225,16 @@ def main():
             checked += 1
         os.environ.pop("DTFFTB_RESHAPE_SHORTCUTS", None)
 
-    # DTFFTB_TRANSPOSE_OVERLAP: a local transposition pipelined with the exchange next to it on a slab-shaped
-    # grid 1 x 1 x P (forward: X->Y local producer of Y->Z; backward: Z->Y exchange feeding Y->X), 3 uneven chunks
-    # (opt-in product feature that has not run on a GPU yet: checked only when DTFFTB_TEST_EXPERIMENTAL=1,
-    # which tools/r02_n2.sh sets, so that the default suite stays the one that was green on B200)
+    # Plan::run_transpose_pair on a slab-shaped grid 1 x 1 x P (forward: X->Y local feeding Y->Z; backward: Z->Y exchange
+    # feeding Y->X): peer-by-peer pipeline when the exchange runs in its copy-engine form
     experimental = os.environ.get("DTFFTB_TEST_EXPERIMENTAL", "0") == "1"
     if experimental and Backend.NVLINK_FUSED in backends:
-        os.environ["DTFFTB_TRANSPOSE_OVERLAP"] = "3"
         dims = [96, 36, 32 * world + 1]  # x = 96: the copy-engine form cuts the blocks into up to 3 slices
         plan = PlanC2C(dims, comm=comm, config=Config(backend=Backend.NVLINK_FUSED, enable_z_slab=False))
-        os.environ.pop("DTFFTB_TRANSPOSE_OVERLAP")
         assert plan.grid_dims == [1, 1, world], plan.grid_dims
+        # the peer-by-peer pipeline runs when the exchange is in its copy-engine form (forced by DTFFTB_FUSED_MODE=dma
+        # at these sizes); with the direct-store kernel the two transpositions run one after the other
+        want_pipelined = 1 if plan.exchange_form(2)["form"] == "copy engines" else 0
         G = P.global_array(dims, np.complex128, kind="random")
         pencils = [oracle_pencil(plan.get_pencil(lay[d])) for d in range(3)]
         x, want = P.pencil_slice(G, pencils[0]), P.pencil_slice(G, pencils[2])
@@ -249,11 +248,11 @@ def main():
             dist.barrier()
             plan.execute(at, bt, Execute.FORWARD)
             sync(plan)
-            assert plan.overlapped_stages == 1, plan.overlapped_stages
+            assert plan.overlapped_stages == want_pipelined, plan.overlapped_stages
             assert np.array_equal(host(bt, np.complex128, want.size).view(np.uint8), want.view(np.uint8)), ("pair fwd", rank)
             plan.execute(bt, ct, Execute.BACKWARD)
             sync(plan)
-            assert plan.overlapped_stages == 1
+            assert plan.overlapped_stages == want_pipelined
             assert np.array_equal(host(ct, np.complex128, x.size).view(np.uint8), x.view(np.uint8)), ("pair bwd", rank)
         assert plan.peer_error() == 0
         for b_ in (ab, bb, cb):

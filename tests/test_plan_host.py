@@ -154,62 +154,6 @@ def test_stage_overlap_chunks_tile_the_transposition(dims, nranks, nchunks):
     Config()._commit()
 
 
-@pytest.mark.parametrize("dims,nranks,nchunks", [((24, 20, 36), 4, 3), ((17, 13, 29), 3, 4), ((32, 8, 16), 8, 8),
-                                                 ((12, 10, 7), 2, 5)])
-def test_transpose_pair_pipelining_geometry(dims, nranks, nchunks):
-    """DTFFTB_TRANSPOSE_OVERLAP (Plan::run_transpose_pair) on a slab-shaped grid 1 x 1 x P, where X<->Y is
-    local and Y<->Z exchanges.  Forward (producer): piece k of the local X->Y writes exactly the source
-    range of chunk k of the Y->Z exchange, and chunk after chunk the exchange delivers the Z pencils.
-    Backward (consumer): piece k of the local Y->X reads only what the members' chunk k of Z->Y has
-    delivered (everything else still holds a sentinel), and the pieces together give the X pencils."""
-    cfg = Config(enable_z_slab=False)
-    plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True), cart_dims=[1, 1, nranks])
-    comm_dims = plans[0].grid_dims
-    assert comm_dims == [1, 1, nranks]
-    G = P.global_array(dims, np.complex128, kind="index")
-    SENT = np.complex128(-7 - 7j)
-    # ---- forward: X -> Y (local, producer) then Y -> Z (exchange) --------------------------------------
-    X = P.scatter_input(G, list(dims), comm_dims, 1)
-    wantY = P.transpose_datatype(G, list(dims), comm_dims, 1)
-    wantZ = P.transpose_datatype(G, list(dims), comm_dims, 2)
-    mid = [np.full(w.size, SENT) for w in wantY]
-    outZ = [np.full(w.size, SENT) for w in wantZ]
-    members = plans[0].describe_exchange(2)["members"]
-    for k in range(nchunks):
-        for r, plan in enumerate(plans):
-            piece = plan.describe_local_piece(1, 2, 0, k, nchunks)
-            P.apply_boxes(X[r], [mid[r]], piece, [0])
-            ch = plan.describe_chunk(2, k, nchunks)
-            lo = ch["chunk_offset"]
-            hi = plan.describe_chunk(2, k + 1, nchunks)["chunk_offset"] if k + 1 < nchunks else mid[r].size
-            # the piece has produced exactly the chunk the exchange is about to read
-            assert not np.any(mid[r][lo:hi] == SENT) and np.all(mid[r][hi:] == SENT), (k, r)
-        for r, plan in enumerate(plans):
-            ch = plan.describe_chunk(2, k, nchunks)
-            P.apply_boxes(mid[r][ch["chunk_offset"]:], outZ, ch["boxes"], members)
-    for r in range(nranks):
-        assert np.array_equal(mid[r], wantY[r]) and np.array_equal(outZ[r], wantZ[r]), r
-    # ---- backward: Z -> Y (exchange) then Y -> X (local, consumer) -------------------------------------
-    Z = P.scatter_input(G, list(dims), comm_dims, -2)
-    wantX = P.transpose_datatype(G, list(dims), comm_dims, -1)
-    mid = [np.full(w.size, SENT) for w in wantY]
-    outX = [np.full(w.size, SENT) for w in wantX]
-    hits = [np.zeros(w.size, np.int32) for w in wantX]
-    members = plans[0].describe_exchange(-2)["members"]
-    for k in range(nchunks):
-        for r, plan in enumerate(plans):  # every member stores its chunk k ...
-            ch = plan.describe_chunk(-2, k, nchunks)
-            P.apply_boxes(Z[r][ch["chunk_offset"]:], mid, ch["boxes"], members)
-        for r, plan in enumerate(plans):  # ... "landed" barrier ... then everybody consumes piece k
-            piece = plan.describe_local_piece(-1, -2, 1, k, nchunks)
-            P.apply_boxes(mid[r], [outX[r]], piece, [0] * len(piece))
-            P.apply_boxes(np.ones(mid[r].size, np.int32), [hits[r]], piece, [0] * len(piece))
-    for r in range(nranks):
-        assert np.array_equal(outX[r], wantX[r]), r  # a piece that read ahead of its chunk would have copied the sentinel
-        assert np.all(hits[r] == 1)
-    Config()._commit()
-
-
 # ---------------------------------------------------------------------------------------------
 # user pencils and bricks
 # ---------------------------------------------------------------------------------------------
