@@ -414,10 +414,14 @@ def run_ours(args):
     tname = f"transpose_tiles_kernel<uint4,{ki['tile_a'] // 32},{ki['tile_b'] // 32},{ki['threads'] // 32}>"
     kernel_name = f"{tname} (one launch per local transposition)"
     forms = {t.name: plan.exchange_form(t) for t, _, _ in order}
-    if R["backend"] == "NVLINK_FUSED" and any(v["form"] == "copy engines" for v in forms.values()):
+    if R["backend"] == "NVLINK_FUSED" and any(v["form"] == "copy engines" for v in forms.values()):  # forced everywhere
         ncop = max(v["copies_per_execute"] for v in forms.values())
         exchange_kernel_name = (f"{tname} packing each peer slice locally + {ncop} strided cudaMemcpy3DAsync copies to the "
                                 "peers' final addresses (+ peer barriers / pairwise flags)")
+    elif R["backend"] == "NVLINK_FUSED" and any(v["form"].startswith("direct-store kernel alone") for v in forms.values()):
+        exchange_kernel_name = (f"timed alone: {tname} with peer-mapped destinations (+ peer barriers); inside dtfft_execute: "
+                                f"{tname} packing each peer slice + strided cudaMemcpy3DAsync copies, pipelined peer by peer "
+                                "with the local transposition next to it")
     elif R["backend"] == "NVLINK_FUSED":
         exchange_kernel_name = f"{tname} with peer-mapped destinations (+ peer barriers)"
     else:

@@ -437,16 +437,22 @@ void overlap_along(const RankLayout& a, const RankLayout& b, int A, long long* l
 }
 }  // namespace
 
-int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage) {
+int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage, int group_size) {
     const RankLayout src = layout_of(sender_src), dst = layout_of(receiver_dst);
     bool tr = false;
     const Box b = intersect_box(src, dst, &tr);
     if (b.empty()) return 1;
-    long long target = 16ll << 20;
+    // Every copy costs ~13 us of its own on B200 (measured: 7 copies of 33.5 MB in 0.444 ms, 14 in 0.538 ms at 8 GPUs;
+    // 1 / 8 copies of 512 / 64 MiB in 0.91 / 0.835 ms at 2 GPUs, profiles/r02e_bench_n8_dma_*.json, r02f_bench_n2_*.json),
+    // so a rank issues about 8 copies per exchange: with many peers the peers themselves pipeline packs and copies and the
+    // blocks travel whole, with few peers the blocks are cut.  Never below DTFFTB_DMA_SUB_BYTES (default 4 MiB) per slice.
+    long long target = 4ll << 20;
     if (const char* e = getenv("DTFFTB_DMA_SUB_BYTES")) target = std::max(1ll, atoll(e));
     long long lo = 0, hi = 0;
     overlap_along(src, dst, src.axis[src.ndims - 1], &lo, &hi);
-    long long n = (b.volume() * base_storage) / target;
+    long long n = 8 / std::max(1, group_size - 1);
+    if (getenv("DTFFTB_DMA_SUB_BYTES")) n = 8;  // explicit slice size: only the cap of 8 applies (tests, A/B runs)
+    n = std::min<long long>(n, (b.volume() * base_storage) / target);
     n = std::min<long long>(n, (hi - lo) / 32);
     return (int)std::max<long long>(1, std::min<long long>(8, n));
 }

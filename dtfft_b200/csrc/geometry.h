@@ -148,8 +148,9 @@ DmaBlock dma_block(const Box& b, bool transposing, long long staging_off);
 // slice s + 1 runs beside the copy of slice s (with few peers a whole block would serialise pack and copy).
 // Sender and receiver derive the same count from what both know: the block's bytes and its extent along that axis
 // (a slice keeps at least 32 elements of it, a full tile width wherever that axis is somebody's fastest one).
-// DTFFTB_DMA_SUB_BYTES (default 16 MiB) is the slice size aimed at; at most 8 slices.
-int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage);
+// About 8 copies per rank and exchange (8 / (group size - 1) slices per block), none below DTFFTB_DMA_SUB_BYTES
+// (default 4 MiB); setting that variable lifts the per-group rule (at most 8 slices per block then).
+int dma_nsub(const Pencil& sender_src, const Pencil& receiver_dst, int64_t base_storage, int group_size);
 // Global index range [lo, hi) of slice s of n of the block (sender_src -> receiver_dst) along that axis (*axis).
 void dma_sub_range(const Pencil& sender_src, const Pencil& receiver_dst, int s, int nsub, int* axis, long long* lo,
                    long long* hi);

@@ -15,9 +15,9 @@ void ReshapeHandle::destroy() {
     dma_pack_.reset();
     dma_self_.reset();
     dma_subs_.clear();
-    dma_ = false;
+    dma_ = dma_standalone_ = false;
     dma_bases_ = nullptr;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kCopyStreams; ++i) {
         if (copy_streams_[i]) cudaStreamDestroy(copy_streams_[i]);
         if (copies_done_[i]) cudaEventDestroy(copies_done_[i]);
         copy_streams_[i] = nullptr, copies_done_[i] = nullptr;
@@ -108,7 +108,7 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
             for (int r = 0; r < P && all_ok; ++r) {
                 for (int i = 0; i < P && all_ok; ++i) {
                     if (i == r) continue;
-                    const int nsub = dma_nsub(send_by_member[(size_t)r], recv_by_member[(size_t)i], es_);
+                    const int nsub = dma_nsub(send_by_member[(size_t)r], recv_by_member[(size_t)i], es_, P);
                     long long bytes = 0;
                     for (int q = 0; q < nsub && all_ok; ++q) {
                         bool tr = false;
@@ -123,8 +123,17 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
             const char* e = getenv("DTFFTB_FUSED_MODE");
             const bool force_dma = e && (e[0] == 'd' || e[0] == 'D');
             const bool force_store = e && (e[0] == 's' || e[0] == 'S');
-            // a copy costs a few microseconds of set-up: below ~1 MiB per peer the single direct-store kernel wins
-            dma_ = all_ok && !force_store && (force_dma || max_block_bytes >= (1ll << 20));
+            // Where the copy-engine form pays (B200, 512^3 c128 cycle, profiles/): on its own it is slower than the
+            // direct-store kernel (every copy costs ~13 us of its own: 0.835 vs 0.787 ms per exchange at 2 GPUs, 0.444 vs
+            // 0.370 ms at 8), but pipelined peer by peer with the local transposition next to it the cycle drops from
+            // 2.20 to 1.91 ms at 2 GPUs; at 8 GPUs the local transpositions are too short to pay for the copies (0.99 vs
+            // 0.89 ms).  So by default it is kept for the pair pipeline of small groups with large blocks, and a lone
+            // transposition runs the direct-store kernel.  DTFFTB_FUSED_MODE = dma forces it everywhere it is possible,
+            // = store switches it off.
+            int max_group = 2;
+            if (const char* g = getenv("DTFFTB_DMA_MAX_GROUP")) max_group = atoi(g);
+            dma_ = all_ok && !force_store && (force_dma || (max_block_bytes >= (8ll << 20) && P <= max_group));
+            dma_standalone_ = dma_ && force_dma;
             if (dma_) {
                 dma_subs_.assign((size_t)P, std::vector<DmaSub>());
                 std::vector<Box> packs, selfs((size_t)P);
@@ -132,7 +141,7 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
                 long long off = 0;
                 for (int i = 0; i < P; ++i) {
                     if (i == me) continue;
-                    const int nsub = dma_nsub(send, recv_by_member[(size_t)i], es_);
+                    const int nsub = dma_nsub(send, recv_by_member[(size_t)i], es_, P);
                     for (int q = 0; q < nsub; ++q) {
                         bool tr = false;
                         const Box b = block_box(send, recv_by_member[(size_t)i], q, nsub, &tr);
@@ -161,7 +170,7 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
         geo_.ttype = ttype, geo_.rtype = rtype, geo_.ndims = ndims;
         geo_.comm_size = P, geo_.comm_rank = me, geo_.members = members;
         geo_.has_exchange = true, geo_.is_fused = true;
-        launches_ = dma_ ? 2 + P : 3;  // barrier + (packs + self | fused kernel) + barrier
+        launches_ = dma_standalone_ ? 2 + P : 3;  // barrier + (packs + self | fused kernel) + barrier
         created_ = true;
         return DTFFT_SUCCESS;
     }
@@ -266,7 +275,8 @@ int ReshapeHandle::peer_bases(void* out, std::vector<void*>* bases) {
 
 int ReshapeHandle::ensure_dma_resources() {
     cudaError_t ce;
-    for (int i = 0; i < 2; ++i) {
+    if (const char* e = getenv("DTFFTB_DMA_STREAMS")) n_copy_streams_ = std::max(1, std::min((int)kCopyStreams, atoi(e)));
+    for (int i = 0; i < n_copy_streams_; ++i) {
         if (!copy_streams_[i]) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -295,7 +305,7 @@ int ReshapeHandle::dma_begin(void* out, cudaStream_t stream) {
     rc = peer_bases(out, &bases);  // collective on the first use of `out`; an identity check afterwards
     if (rc) return rc;
     dma_bases_ = &maps_.find(out)->second.bases;
-    copy_used_[0] = copy_used_[1] = false;
+    for (int c = 0; c < kCopyStreams; ++c) copy_used_[c] = false;
     return ctx_.peers->barrier(members_, 2 * (comm_id_ - 1), stream);  // every member's `out` is free
 }
 
@@ -347,7 +357,7 @@ int ReshapeHandle::dma_wait(int source, int sub, cudaStream_t stream) {
 
 int ReshapeHandle::dma_end(cudaStream_t stream, bool landed_barrier) {
     if (!dma_mode()) return DTFFTB_ERROR_INTERNAL;
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < kCopyStreams; ++c) {
         if (!copy_used_[c]) continue;
         cudaError_t ce = cudaEventRecord(copies_done_[c], copy_streams_[c]);
         if (ce != cudaSuccess) return cuda_error(ce);
@@ -456,7 +466,7 @@ int ReshapeHandle::fused_chunk(void* in, void* out, int k, int nchunks, int max_
 int ReshapeHandle::execute(void* in, void* out, cudaStream_t stream, void* aux) {
     if (!created_) return DTFFT_ERROR_PLAN_NOT_CREATED;
     if (!has_exchange_) return pack_->execute(in, out, stream, 0, false);
-    if (backend_ == BACKEND_NVLINK_FUSED) return dma_ ? execute_dma(in, out, stream, aux) : execute_fused(in, out, stream);
+    if (backend_ == BACKEND_NVLINK_FUSED) return dma_standalone_ ? execute_dma(in, out, stream, aux) : execute_fused(in, out, stream);
     int rc;
     if (nccl_->is_pipelined()) {
         if (!aux) return DTFFT_ERROR_INVALID_AUX;

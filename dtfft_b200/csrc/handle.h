@@ -114,12 +114,13 @@ public:
     //     dma_signal(p, q) / dma_wait(r, q, s)  per-pair "slice has landed" flags instead of the group barrier
     //     dma_end(s, barrier)          join the copy streams (+ "all landed" barrier)
     bool dma_mode() const { return created_ && has_exchange_ && backend_ == BACKEND_NVLINK_FUSED && dma_; }
+    bool dma_standalone() const { return dma_mode() && dma_standalone_; }
     int dma_begin(void* out, cudaStream_t stream);
     int dma_send(const void* in, void* out, void* aux, int peer, int sub, cudaStream_t stream);
     // slices of the block I send to member `peer` / receive from member `source` (geometry.h: dma_nsub)
     int n_subs_to(int peer) const { return peer == me_ ? 1 : (int)dma_subs_[(size_t)peer].size(); }
     int n_subs_from(int source) const {
-        return source == me_ ? 1 : dma_nsub(send_by_member_[(size_t)source], recv_by_member_[(size_t)me_], es_);
+        return source == me_ ? 1 : dma_nsub(send_by_member_[(size_t)source], recv_by_member_[(size_t)me_], es_, (int)members_.size());
     }
     int dma_self(const void* in, void* out, cudaStream_t stream);
     int dma_advance_signals(cudaStream_t stream) { return ctx_.peers->advance_epoch(members_, 6 + (comm_id_ - 1), stream); }
@@ -173,19 +174,25 @@ private:
     };
     std::map<const void*, PeerMap> maps_;
     // copy-engine form
-    bool dma_ = false;
+    bool dma_ = false;             // the copy-engine form is set up: pair pipelines use it
+    bool dma_standalone_ = false;  // ... and so does a lone execute() (DTFFTB_FUSED_MODE=dma)
     struct DmaSub {
         DmaBlock blk;
         int pack_index = -1;  // box of dma_pack_ (and event) of this slice; -1 = empty
     };
     std::vector<std::vector<DmaSub>> dma_subs_;  // [member][slice]
-    int copy_stream_of(int peer) const { return ((peer - me_ + (int)members_.size()) % (int)members_.size()) & 1; }
+    int copy_stream_of(int peer) const {
+        const int P = (int)members_.size();
+        return ((peer - me_ + P) % P + n_copy_streams_ - 1) % n_copy_streams_;
+    }
     std::unique_ptr<Kernel> dma_pack_;      // in -> staging, one launch per peer
     std::unique_ptr<Kernel> dma_self_;      // my own block, in -> out
-    cudaStream_t copy_streams_[2] = {nullptr, nullptr};
+    static constexpr int kCopyStreams = 8;
+    int n_copy_streams_ = 2;  // DTFFTB_DMA_STREAMS (1..8): peers are dealt round over this many copy streams
+    cudaStream_t copy_streams_[kCopyStreams] = {};
     std::vector<cudaEvent_t> pack_done_;    // per slice
-    cudaEvent_t copies_done_[2] = {nullptr, nullptr};
-    bool copy_used_[2] = {false, false};
+    cudaEvent_t copies_done_[kCopyStreams] = {};
+    bool copy_used_[kCopyStreams] = {};
     const std::vector<void*>* dma_bases_ = nullptr;  // of the `out` of the exchange in flight (dma_begin)
     int execute_dma(void* in, void* out, cudaStream_t stream, void* aux);
     int ensure_dma_resources();

@@ -1415,7 +1415,7 @@ int Plan::describe_dma(int ttype, std::vector<int>* members, int* me, std::vecto
     const Pencil& send = hs.send[(size_t)hs.me];
     long long off = 0;
     for (size_t i = 0; i < hs.members.size(); ++i) {
-        const int nsub = (int)i == hs.me ? 1 : dma_nsub(send, hs.recv[i], hs.es);
+        const int nsub = (int)i == hs.me ? 1 : dma_nsub(send, hs.recv[i], hs.es, (int)hs.members.size());
         for (int q = 0; q < nsub; ++q) {
             DmaEntry e;
             e.member = (int)i, e.sub = q, e.nsub = nsub;
@@ -1446,7 +1446,7 @@ int Plan::describe_peer_piece(int t_local, int t_exchange, int side, int peer, i
     // side 1: it precedes: block (the sender's source -> my pencil in between)
     const Pencil& x_src = side == 0 ? hx.send[(size_t)hx.me] : hx.send[(size_t)peer];
     const Pencil& x_dst = side == 0 ? hx.recv[(size_t)peer] : hx.recv[(size_t)hx.me];
-    const int nsub = peer == hx.me ? 1 : dma_nsub(x_src, x_dst, hx.es);
+    const int nsub = peer == hx.me ? 1 : dma_nsub(x_src, x_dst, hx.es, (int)hx.members.size());
     if (nsub_out) *nsub_out = nsub;
     if (sub < 0 || sub >= nsub) return DTFFT_ERROR_INVALID_USAGE;
     *box = local_box_for_block(hl.send[0], hl.recv[0], x_src, x_dst, sub, nsub);

@@ -102,7 +102,8 @@ public:
     }
     int64_t graph_replays() const { return stat_graph_replays_; }
     int64_t fallbacks() const { return stat_fallbacks_; }
-    // How one transposition moves its data: 0 local kernel only, 1 NCCL, 2 direct-store kernel, 3 copy engines
+    // How one transposition moves its data: 0 local kernel only, 1 NCCL, 2 direct-store kernel, 3 copy engines,
+    // 4 direct-store kernel on its own, copy engines when pipelined with the local transposition next to it
     // (*n_slices = copies this rank issues per execute).
     int exchange_form(int ttype, int* form, int* n_slices) const {
         auto it = handles_.find(ttype);
@@ -113,7 +114,7 @@ public:
         else if (h.backend() != BACKEND_NVLINK_FUSED) *form = 1;
         else if (!h.dma_mode()) *form = 2;
         else {
-            *form = 3;
+            *form = h.dma_standalone() ? 3 : 4;
             for (int i = 0; i < h.n_members(); ++i)
                 if (i != h.my_index()) *n_slices += h.n_subs_to(i);
         }

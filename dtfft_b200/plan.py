@@ -561,7 +561,8 @@ class Plan:
         f, n = C.c_int(0), C.c_int(0)
         _check(_lib.lib().dtfftb_plan_get_exchange_form(self._h, int(transpose_type), C.byref(f), C.byref(n)),
                "dtfftb_plan_get_exchange_form")
-        names = {0: "local kernel", 1: "nccl", 2: "direct-store kernel", 3: "copy engines"}
+        names = {0: "local kernel", 1: "nccl", 2: "direct-store kernel", 3: "copy engines",
+                 4: "direct-store kernel alone, copy engines in pair pipelines"}
         return {"form": names.get(f.value, str(f.value)), "copies_per_execute": n.value}
 
     @property

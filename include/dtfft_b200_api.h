@@ -362,7 +362,8 @@ dtfft_error_t dtfftb_plan_set_graphs(dtfft_plan_t plan, int enable);
 dtfft_error_t dtfftb_plan_get_graph_replays(dtfft_plan_t plan, int64_t* n_replays);
 /* How one transposition of the plan moves its data on this rank: *form = 0 local kernel only (one rank in its
  * communicator), 1 NCCL (pack -> ncclSend/Recv -> unpack), 2 NVLINK_FUSED direct-store kernel, 3 NVLINK_FUSED copy-engine
- * form (pack + one strided 3-D copy per peer slice; *n_slices = copies per execute). */
+ * form (pack + one strided 3-D copy per peer slice; *n_slices = copies per execute), 4 direct-store kernel when run on
+ * its own and the copy-engine form when pipelined with the local transposition next to it in dtfft_execute. */
 dtfft_error_t dtfftb_plan_get_exchange_form(dtfft_plan_t plan, int transpose_type, int* form, int* n_slices);
 /* NVLINK_FUSED: how many transpositions / reshapes of this plan ran on the NCCL stand-in because a caller's
  * buffer could not be shared through cudaIpc (stream-ordered or virtual-memory allocations). */
