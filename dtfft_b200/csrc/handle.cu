@@ -126,11 +126,11 @@ int ReshapeHandle::create(const HandleContext& ctx, int ttype, int rtype, int co
             // Where the copy-engine form pays (B200, 512^3 c128 cycle, profiles/): on its own it is slower than the
             // direct-store kernel (every copy costs ~13 us of its own: 0.835 vs 0.787 ms per exchange at 2 GPUs, 0.444 vs
             // 0.370 ms at 8), but pipelined peer by peer with the local transposition next to it the cycle drops from
-            // 2.20 to 1.91 ms at 2 GPUs; at 8 GPUs the local transpositions are too short to pay for the copies (0.99 vs
-            // 0.89 ms).  So by default it is kept for the pair pipeline of small groups with large blocks, and a lone
-            // transposition runs the direct-store kernel.  DTFFTB_FUSED_MODE = dma forces it everywhere it is possible,
-            // = store switches it off.
-            int max_group = 2;
+            // 2.20 to 1.91 ms at 2 GPUs and from 1.51 to 1.37 ms at 4; at 8 GPUs the local transpositions are too short to
+            // pay for the copies (0.99 vs 0.89 ms).  So by default it is kept for the pair pipeline of groups of up to 4
+            // with large blocks, and a lone transposition runs the direct-store kernel.  DTFFTB_FUSED_MODE = dma forces it
+            // everywhere it is possible, = store switches it off.
+            int max_group = 4;
             if (const char* g = getenv("DTFFTB_DMA_MAX_GROUP")) max_group = atoi(g);
             dma_ = all_ok && !force_store && (force_dma || (max_block_bytes >= (8ll << 20) && P <= max_group));
             dma_standalone_ = dma_ && force_dma;
