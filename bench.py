@@ -297,7 +297,8 @@ def run_ours(args):
             want = [expected_pencil(torch, pen[d], d, dims, a.device) for d in range(3)]
 
             def step(name, fn, src, dst, d_dst):
-                dst.fill_(-7.0)  # a stale result of an earlier step must not pass
+                dst.fill_(-7.0)  # a stale result of an earlier step must not pass ...
+                aux.fill_(0x5B)  # ... nor a stale intermediate pencil / staging block of an earlier step
                 stream.synchronize()
                 barrier()
                 fn()
