@@ -51,6 +51,8 @@ struct BlockDesc {
     const unsigned long long* abort;  // blocks[0] only: non-null -> sticky peer-error word; when set the kernel stores nothing
     int n0, n1, n2;       // extents along a, b, c
     int tiles0, tiles1;   // tiles along a and b
+    int bshift;           // family T: tiles along b start `bshift` elements BEFORE the box, so that every tile boundary falls
+                          // on a 128-byte line of the destination (0 = box origin already aligned, or rows not alignable)
     FastDiv div0, div1;   // fast division by tiles0 / tiles1
 };
 

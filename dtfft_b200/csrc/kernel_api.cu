@@ -127,7 +127,7 @@ int dtfftb_kernel_dump_table(dtfftb_kernel_t kernel, int unit, int neighbor, int
         o[7] = d.item_begin, o[8] = d.shuffle, o[9] = d.n0, o[10] = d.n1, o[11] = d.n2, o[12] = d.tiles0, o[13] = d.tiles1;
         o[14] = d.div0.mul, o[15] = d.div0.shr, o[16] = d.div1.mul, o[17] = d.div1.shr;
         o[18] = d.out_base ? (int64_t)((uintptr_t)d.out_base >> 40) - 1 : -1;
-        o[19] = 0;
+        o[19] = d.bshift;
     }
     return DTFFT_SUCCESS;
 }

@@ -373,6 +373,7 @@ int Kernel::create_boxes(Family family, int64_t base_storage, const std::vector<
 }
 
 int Kernel::rebuild_tables() {
+    if (const char* e = getenv("DTFFTB_ALIGN_TILES")) align_b_ = atoi(e) != 0;
     if (d_blocks_) cudaFree(d_blocks_);
     d_blocks_ = nullptr;
     host_tables_.clear();
@@ -391,7 +392,16 @@ int Kernel::rebuild_tables() {
         d.is1 = b.is1, d.is2 = b.is2, d.os0 = b.os0, d.os1 = b.os1, d.os2 = b.os2;
         d.n0 = (int)b.n0, d.n1 = (int)b.n1, d.n2 = (int)b.n2;
         d.tiles0 = (int)((b.n0 + t0 - 1) / t0);
-        d.tiles1 = (int)((b.n1 + t1 - 1) / t1);
+        d.bshift = 0;
+        if (family_ == FAM_T && align_b_) {
+            // tiles along the output-contiguous axis start on 128-byte lines of the destination when every row of the box
+            // has the same misalignment (outer strides are multiples of a line); bases are taken as line-aligned here and
+            // checked at launch (Kernel::launch passes `noshift` otherwise)
+            const long long L = 128 / es_;
+            const bool rows_alike = (b.n0 == 1 || (b.os0 % L) == 0) && (b.n2 == 1 || (b.os2 % L) == 0);
+            if (rows_alike && b.n1 * es_ >= 256) d.bshift = (int)(((b.out_off % L) + L) % L);
+        }
+        d.tiles1 = (int)((b.n1 + d.bshift + t1 - 1) / t1);
         d.div0 = FastDiv::make((unsigned)d.tiles0);
         d.div1 = FastDiv::make((unsigned)d.tiles1);
         d.item_begin = begin;
@@ -584,9 +594,12 @@ int Kernel::launch(const DeviceTable& t, int unit, const void* in, void* out, cu
         // to the element size (family R narrows its unit instead, pick_unit)
         const uintptr_t mask = (uintptr_t)es_ - 1;
         if ((reinterpret_cast<uintptr_t>(in) & mask) || (reinterpret_cast<uintptr_t>(out) & mask)) return DTFFT_ERROR_INVALID_USAGE;
-        for (void* p : peer_out_)
+        bool noshift = (reinterpret_cast<uintptr_t>(out) & 127) != 0;
+        for (void* p : peer_out_) {
             if (reinterpret_cast<uintptr_t>(p) & mask) return DTFFT_ERROR_INVALID_USAGE;
-        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);
+            noshift |= (reinterpret_cast<uintptr_t>(p) & 127) != 0;
+        }
+        ce = launch_transpose((int)es_, tile_, in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream, noshift);
     } else {
         const int slot = unit == 4 ? 0 : unit == 8 ? 1 : 2;
         ce = launch_rows(unit, tx_slot_[slot], in, out, d_blocks_ + t.offset, t.nblocks, t.total_items, cap, stream);

@@ -122,6 +122,7 @@ private:
     TileCfg tile_{1, 1, 8};
     std::vector<AutotuneEntry>* autotune_log_ = nullptr;
     const unsigned long long* abort_flag_ = nullptr;
+    bool align_b_ = true;  // DTFFTB_ALIGN_TILES=0: tile grid anchored at the box origin (A/B of BlockDesc::bshift)
     int tx_ = 32;
     int tx_slot_[3] = {32, 32, 32};
     int unit_geo_ = 4;  // widest unit the geometry allows (family R)

@@ -113,7 +113,7 @@ __device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks,
 template <typename T, int KA, int KB, int ROWS>
 __global__ void __launch_bounds__(32 * ROWS)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
-                           int nblocks, long long total_items) {
+                           int nblocks, long long total_items, int noshift) {
     constexpr int TA = 32 * KA, TB = 32 * KB;
     constexpr int PITCH = TB + 1;
     constexpr int LD_ROWS = TB / ROWS;  // b-rows each thread loads
@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(32 * ROWS)
         const long long is1 = d.is1, os0 = d.os0;
         const T* src = (d.in_base ? reinterpret_cast<const T*>(d.in_base) : in) + d.in_off + (long long)p.c * d.is2;
         T* dst = (d.out_base ? reinterpret_cast<T*>(d.out_base) : out) + d.out_off + (long long)p.c * d.os2;
-        const int a0 = p.t0 * TA, b0 = p.t1 * TB;
+        // Destination runs that start off a 128-byte line (uneven splits: 250 x 8 B ...) would make every tile boundary
+        // split a line between two warps: partial-line stores, ruinous over NVLink (config 5, Y->Z: 204 GB/s).  The
+        // table builder shifts the tile grid back by d.bshift elements instead; the first tile is masked at its start.
+        const int a0 = p.t0 * TA, b0 = p.t1 * TB - (noshift ? 0 : d.bshift);
 
         T regs[LD_ROWS][KA];
 #pragma unroll
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int a = a0 + tx + 32 * k;
-                if (a < n0 && b < n1) regs[j][k] = ld_global(src + a + (long long)b * is1);
+                if (a < n0 && b >= 0 && b < n1) regs[j][k] = ld_global(src + a + (long long)b * is1);
             }
         }
 #pragma unroll
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int b = b0 + tx + 32 * k;
-                if (a < n0 && b < n1) st_global(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k]);
+                if (a < n0 && b >= 0 && b < n1) st_global(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k]);
             }
         }
         __syncthreads();
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 
 template <int ES, int KA, int KB, int ROWS>
 cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nblocks, long long total, int grid_cap,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int noshift) {
     using T = typename ElemT<ES>::type;
     constexpr size_t smem = (size_t)(32 * KA) * (32 * KB + 1) * ES;
     auto kern = transpose_tiles_kernel<T, KA, KB, ROWS>;
@@ -190,15 +193,15 @@ cudaError_t launch_T(const void* in, void* out, const BlockDesc* blocks, int nbl
     }
     long long g = total < grid_cap ? total : grid_cap;
     kern<<<(unsigned)g, dim3(32, ROWS), smem, stream>>>(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out),
-                                                        blocks, nblocks, total);
+                                                        blocks, nblocks, total, noshift);
     return cudaGetLastError();
 }
 
 template <int ES>
 cudaError_t dispatch_T(TileCfg c, const void* in, void* out, const BlockDesc* b, int nb, long long total, int cap,
-                       cudaStream_t s) {
+                       cudaStream_t s, int noshift) {
 #define DTFFTB_T_CASE(KA_, KB_, R_) \
-    if (c.ka == KA_ && c.kb == KB_ && c.rows == R_) return launch_T<ES, KA_, KB_, R_>(in, out, b, nb, total, cap, s);
+    if (c.ka == KA_ && c.kb == KB_ && c.rows == R_) return launch_T<ES, KA_, KB_, R_>(in, out, b, nb, total, cap, s, noshift);
     DTFFTB_T_CASE(1, 1, 4)
     DTFFTB_T_CASE(1, 1, 8)
     DTFFTB_T_CASE(1, 1, 16)
@@ -291,12 +294,12 @@ bool transpose_cfg_supported(int es, TileCfg c) {
 }
 
 cudaError_t launch_transpose(int es, TileCfg cfg, const void* in, void* out, const BlockDesc* d_blocks, int nblocks,
-                             long long total_items, int grid_cap, cudaStream_t stream) {
+                             long long total_items, int grid_cap, cudaStream_t stream, bool noshift) {
     if (total_items <= 0) return cudaSuccess;
     switch (es) {
-        case 4: return dispatch_T<4>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
-        case 8: return dispatch_T<8>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
-        case 16: return dispatch_T<16>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream);
+        case 4: return dispatch_T<4>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, noshift ? 1 : 0);
+        case 8: return dispatch_T<8>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, noshift ? 1 : 0);
+        case 16: return dispatch_T<16>(cfg, in, out, d_blocks, nblocks, total_items, grid_cap, stream, noshift ? 1 : 0);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -15,8 +15,10 @@ struct TileCfg {
 
 // Family T: out[b-contiguous] <- in[a-contiguous] for every block of the table.
 // `es` = element bytes (4, 8, 16).  Table lives in device memory.
+// `noshift`: ignore BlockDesc::bshift (a base pointer of this launch is not 128-byte aligned, so the shifted tile grid
+// would not align anything; the table still covers every element, a few tiles are empty).
 cudaError_t launch_transpose(int es, TileCfg cfg, const void* in, void* out, const BlockDesc* d_blocks,
-                             int nblocks, long long total_items, int grid_cap, cudaStream_t stream);
+                             int nblocks, long long total_items, int grid_cap, cudaStream_t stream, bool noshift = false);
 
 // Family R: row copy in units of `unit` bytes (4, 8, 16); `tx` = threads along the row
 // (power of two, 8..256).  Descriptors are pre-scaled to units.

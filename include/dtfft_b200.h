@@ -152,9 +152,10 @@ int dtfftb_kernel_autotune_report(dtfftb_kernel_t kernel, const void* in, void* 
  * dtfftb_kernel_dump_table: the work-item table of one launch -- all peers (`neighbor` = 0) or one
  * (1-based); `unit` = 4 / 8 / 16 selects the access width of the row-copy family (ignored by the
  * transpose family).  rows = 20 x cap int64 per block: in_off out_off is1 is2 os0 os1 os2
- * item_begin shuffle n0 n1 n2 tiles0 tiles1 div0.mul div0.shr div1.mul div1.shr dest reserved
+ * item_begin shuffle n0 n1 n2 tiles0 tiles1 div0.mul div0.shr div1.mul div1.shr dest bshift
  * (offsets / strides in `unit`s for the row-copy family, in elements for the transpose family;
- * dest = index of the destination buffer or -1 for the launch's `out`).  launch[3] = (KA, KB, ROWS)
+ * dest = index of the destination buffer or -1 for the launch's `out`; bshift = elements by which the tile grid of the
+ * transpose family starts before the box along b, so that tile boundaries fall on 128-byte lines of the destination).  launch[3] = (KA, KB, ROWS)
  * of transpose_tiles_kernel or (TX, TY, rows per thread) of rows_copy_kernel. */
 int dtfftb_kernel_create_dry(dtfftb_kernel_t* kernel, int ndims, const int32_t* dims, int kernel_type,
                              int64_t base_storage, const int32_t* neighbor_data, int n_neighbors);

@@ -6,7 +6,7 @@ tile bounds -- so that a CPU box can check that every table makes the kernels mo
 elements the oracle says, each exactly once.  Test infrastructure only."""
 import numpy as np
 
-IN_OFF, OUT_OFF, IS1, IS2, OS0, OS1, OS2, ITEM_BEGIN, SHUFFLE, N0, N1, N2, TILES0, TILES1, D0MUL, D0SHR, D1MUL, D1SHR, DEST = range(19)
+IN_OFF, OUT_OFF, IS1, IS2, OS0, OS1, OS2, ITEM_BEGIN, SHUFFLE, N0, N1, N2, TILES0, TILES1, D0MUL, D0SHR, D1MUL, D1SHR, DEST, BSHIFT = range(20)
 
 
 def _fast_div(n, mul, shr):
@@ -37,7 +37,7 @@ def _decode(d, item):
     return t0, t1, q1
 
 
-def run_table(table, family, src, dsts, counts=None, grid=None):
+def run_table(table, family, src, dsts, counts=None, grid=None, noshift=False):
     """Emulate one launch.  ``src`` flat array in kernel units (elements for family 'T', access units
     for family 'R'); ``dsts`` = {dest index: flat array} with -1 = the launch's ``out``.
     ``counts`` (same keys) are incremented once per written unit.  ``grid`` = number of CTAs of the
@@ -61,7 +61,10 @@ def run_table(table, family, src, dsts, counts=None, grid=None):
             t0, t1, c = _decode(d, item)
             assert 0 <= t0 < d[TILES0] and 0 <= t1 < d[TILES1] and 0 <= c < d[N2], (item, t0, t1, c)
             a = np.arange(t0 * ta, min((t0 + 1) * ta, d[N0]), dtype=np.int64)[:, None]
-            b = np.arange(t1 * tb, min((t1 + 1) * tb, d[N1]), dtype=np.int64)[None, :]
+            # family T: the tile grid along b starts BSHIFT elements before the box (line-aligned tile boundaries);
+            # `noshift` is the launch-time fallback for misaligned base pointers
+            sh = d[BSHIFT] if (family == "T" and not noshift) else 0
+            b = np.arange(max(t1 * tb - sh, 0), min((t1 + 1) * tb - sh, d[N1]), dtype=np.int64)[None, :]
             if a.size == 0 or b.size == 0:
                 continue
             iidx = d[IN_OFF] + c * d[IS2] + a + b * d[IS1]

@@ -259,3 +259,44 @@ def test_every_tile_configuration(tile, es):
             assert k.dump_table(unit=es)["launch"] == list(tile)
             _check(k, es, kt, dims, src, n, None, 0, grid=61)
             k.destroy()
+
+
+@pytest.mark.parametrize("es,zcounts,ny,nx", [(8, [40, 56], 64, 24), (16, [36, 60], 32, 16), (4, [72, 88], 64, 8), (8, [250, 262], 32, 3)])
+def test_tile_grid_is_aligned_to_destination_lines(es, zcounts, ny, nx):
+    """Uneven splits make destination runs start off a 128-byte line (BASELINE config 5: 250 x 8 B).  The table builder
+    then starts the tile grid BSHIFT elements before the box so that every tile boundary along the output-contiguous axis
+    falls on a line of the destination (kernels.cu: b0 = t1 * TB - bshift, first tile masked at its start).  Both the
+    shifted grid and the launch-time fallback for misaligned base pointers (`noshift`) must move exactly the box's
+    elements, each once."""
+    G = len(zcounts)
+    nz = sum(zcounts)
+    L = 128 // es
+    nyl = ny // G
+    rng = np.random.default_rng(3)
+    for d in range(G):
+        z0 = sum(zcounts[:d])
+        boxes = [[nyl, zcounts[d], nx, p * nyl, z0, ny, ny * zcounts[d], nz * nx, 1, nz] for p in range(G)]
+        k = Kernel().create_boxes_dry(2, es, boxes, remote_peers=True)
+        table = k.dump_table(unit=es)
+        tb = 32 * table["launch"][1]
+        src = rng.integers(1, 2 ** 30, size=ny * zcounts[d] * nx).astype(np.int64)
+        want = [np.zeros(nz * nx * nyl, np.int64) for _ in range(G)]
+        P.apply_boxes(src, want, boxes, list(range(G)))
+        shifted = 0
+        for blk in table["blocks"]:
+            assert blk[E.BSHIFT] == blk[E.OUT_OFF] % L  # rows of these boxes are all misaligned alike
+            shifted += blk[E.BSHIFT] > 0
+            # every tile boundary inside the run is a multiple of a line in destination elements
+            for t1 in range(1, int(blk[E.TILES1])):
+                assert (blk[E.OUT_OFF] + t1 * tb - blk[E.BSHIFT]) % L == 0
+            assert blk[E.TILES1] == -(-(blk[E.N1] + blk[E.BSHIFT]) // tb)
+        if z0 % L:
+            assert shifted == len(table["blocks"])
+        for noshift in (False, True):
+            dsts = {p: np.zeros(nz * nx * nyl, np.int64) for p in range(G)}
+            cnts = {p: np.zeros(nz * nx * nyl, np.int32) for p in range(G)}
+            E.run_table(table, "T", src, dsts, cnts, grid=53, noshift=noshift)
+            for p in range(G):
+                assert np.array_equal(dsts[p], want[p]), (d, p, noshift)
+                assert np.array_equal(cnts[p] == 1, want[p] != 0) and cnts[p].max() <= 1
+        k.destroy()

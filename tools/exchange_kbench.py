@@ -36,6 +36,22 @@ def boxes_for(d, G, n):
     return rows
 
 
+def uneven_case(G, zcounts, ny, nx):
+    """Y -> Z like config 5 (768 x 512 x 1024 f64 bricks: Y pencils 512 x {250|262} x 384, Z pencils 1024 x 384 x 128):
+    the z ranges the ranks own are not multiples of a 128-byte line, so every destination run starts misaligned.
+    Returns (boxes per device, local elements per device, Z-pencil elements)."""
+    nz = sum(zcounts)
+    zstart = [sum(zcounts[:i]) for i in range(G)]
+    nyl = ny // G
+    out = []
+    for d in range(G):
+        rows = []
+        for p in range(G):
+            rows.append([nyl, zcounts[d], nx, p * nyl, zstart[d], ny, ny * zcounts[d], nz * nx, 1, nz])
+        out.append(rows)
+    return out, [ny * zcounts[d] * nx for d in range(G)], nz * nx * nyl
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--devices", type=int, default=torch.cuda.device_count())
@@ -44,7 +60,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--tiles", default="1,2,8;2,2,8;2,1,8;1,4,16;1,1,8", help="ka,kb,rows;...")
     ap.add_argument("--check", action="store_true", help="verify the landed Z pencils (index-encoded)")
+    ap.add_argument("--uneven", default="", help="z counts per device, e.g. 250,262: config-5-like 8-byte case (512 x z x 384)")
     args = ap.parse_args()
+    if args.uneven:
+        return uneven(args)
     G, n = args.devices, args.n
     rt = ctypes.CDLL("libcudart.so.12")
     for d in range(G):
@@ -116,6 +135,65 @@ def main():
                 ok = ok and bool(torch.equal(v[:, 0], want)) and bool(torch.equal(v[:, 1], ~want))
             rec["landed_bit_exact"] = ok
         print(json.dumps(rec), flush=True)
+        for k in kernels:
+            k.destroy()
+
+
+def uneven(args):
+    zc = [int(v) for v in args.uneven.split(",")]
+    G = len(zc)
+    es, ny, nx = 8, 512, 384
+    rt = ctypes.CDLL("libcudart.so.12")
+    for d in range(G):
+        torch.cuda.set_device(d)
+        for p in range(G):
+            if p != d:
+                rt.cudaDeviceEnablePeerAccess(p, 0)
+    boxes, nloc, nz_elems = uneven_case(G, zc, ny, nx)
+    src, dst, streams = [], [], []
+    for d in range(G):
+        torch.cuda.set_device(d)
+        src.append(torch.arange(nloc[d], dtype=torch.int64, device="cuda") + (d << 40))
+        dst.append(torch.zeros(nz_elems, dtype=torch.int64, device="cuda"))
+        streams.append(torch.cuda.Stream(device=d))
+    for tile in args.tiles.split(";"):
+        ka, kb, rows = (int(v) for v in tile.split(","))
+        kernels = []
+        for d in range(G):
+            torch.cuda.set_device(d)
+            k = Kernel().create_boxes(2, es, boxes[d], out_bases=[dst[p] for p in range(G)])
+            k.set_tile(ka, kb, rows)
+            kernels.append(k)
+
+        def launch_all():
+            for d in range(G):
+                torch.cuda.set_device(d)
+                kernels[d].execute_all(src[d], dst[d], streams[d].cuda_stream)
+
+        for _ in range(args.warmup):
+            launch_all()
+        for d in range(G):
+            torch.cuda.synchronize(d)
+        ev = []
+        for d in range(G):
+            torch.cuda.set_device(d)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(streams[d])
+            ev.append((e0, e1))
+        for _ in range(args.iters):
+            launch_all()
+        for d in range(G):
+            torch.cuda.set_device(d)
+            ev[d][1].record(streams[d])
+        ms = 0.0
+        for d in range(G):
+            torch.cuda.synchronize(d)
+            ms = max(ms, ev[d][0].elapsed_time(ev[d][1]) / args.iters)
+        remote = max(nloc) * es * (G - 1) // G
+        print(json.dumps({"what": "config-5-like Y_TO_Z exchange kernel alone (8-byte elements, 512 x z x 384)", "z_counts": zc,
+                          "devices": G, "tile": [32 * ka, 32 * kb], "threads": 32 * rows, "ms": ms,
+                          "remote_bytes_per_gpu": remote, "GBps_per_direction": remote / (ms * 1e-3) / 1e9,
+                          "run_bytes": [z * es for z in zc], "info": kernels[0].info()}), flush=True)
         for k in kernels:
             k.destroy()
 
