@@ -30,35 +30,45 @@ template <> struct ElemT<8> { using type = uint2; };
 template <> struct ElemT<16> { using type = uint4; };
 
 // Payload accesses name the global state space explicitly: block bases come out of the descriptor table
-// (local or peer-mapped HBM), which would otherwise make them generic-space LD / ST in SASS.
+// (local or peer-mapped HBM), which would otherwise make them generic-space LD / ST in SASS.  The bounds predicate
+// travels INTO the instruction (@p ld.global ...): a C++ `if` around inline asm cannot be if-converted and would put a
+// branch around every load of a tile, which cost the 4-byte permutes 7 % (16 loads per thread; profiles/r02k_kbench_quick.txt).
 template <typename T>
-__device__ __forceinline__ T ld_global(const T* p) {
+__device__ __forceinline__ T ld_global_if(const T* p, bool pred) {
+    const unsigned pr = pred ? 1u : 0u;
     if constexpr (sizeof(T) == 16) {
         uint4 v;
-        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+            : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "r"(pr));
         return *reinterpret_cast<T*>(&v);
     } else if constexpr (sizeof(T) == 8) {
         uint2 v;
-        asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.v2.u32 {%0, %1}, [%2];\n\t}"
+            : "=r"(v.x), "=r"(v.y) : "l"(p), "r"(pr));
         return *reinterpret_cast<T*>(&v);
     } else {
         unsigned v;
-        asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pr));
         return *reinterpret_cast<T*>(&v);
     }
 }
 
 template <typename T>
-__device__ __forceinline__ void st_global(T* p, const T& val) {
+__device__ __forceinline__ void st_global_if(T* p, const T& val, bool pred) {
+    const unsigned pr = pred ? 1u : 0u;
     if constexpr (sizeof(T) == 16) {
         const uint4 v = *reinterpret_cast<const uint4*>(&val);
-        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(pr)
+                     : "memory");
     } else if constexpr (sizeof(T) == 8) {
         const uint2 v = *reinterpret_cast<const uint2*>(&val);
-        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(v.x),
+                     "r"(v.y), "r"(pr)
+                     : "memory");
     } else {
         const unsigned v = *reinterpret_cast<const unsigned*>(&val);
-        asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pr) : "memory");
     }
 }
 
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int a = a0 + tx + 32 * k;
-                if (a < n0 && b >= 0 && b < n1) regs[j][k] = ld_global(src + a + (long long)b * is1);
+                regs[j][k] = ld_global_if(src + a + (long long)b * is1, a < n0 && b >= 0 && b < n1);
             }
         }
 #pragma unroll
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int b = b0 + tx + 32 * k;
-                if (a < n0 && b >= 0 && b < n1) st_global(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k]);
+                st_global_if(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k], a < n0 && b >= 0 && b < n1);
             }
         }
         __syncthreads();
@@ -247,12 +257,12 @@ __global__ void __launch_bounds__(kRowsThreads)
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                if (row < n1) regs[r] = ld_global(src + col + (long long)row * is1);
+                regs[r] = ld_global_if(src + col + (long long)row * is1, row < n1);
             }
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                if (row < n1) st_global(dst + col + (long long)row * os1, regs[r]);
+                st_global_if(dst + col + (long long)row * os1, regs[r], row < n1);
             }
         }
     }
