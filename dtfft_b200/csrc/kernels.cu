@@ -120,8 +120,10 @@ __device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks,
 // ---------------------------------------------------------------------------------
 // Family T
 // ---------------------------------------------------------------------------------
+// 512-thread instantiations must keep three CTAs per SM (<= 42 registers): the 8-byte permutes lost 15 % when the
+// build used 50 (profiles/r02_kbench_quick.txt vs r02a_kbench_hint0.txt).
 template <typename T, int KA, int KB, int ROWS>
-__global__ void __launch_bounds__(32 * ROWS)
+__global__ void __launch_bounds__(32 * ROWS, (ROWS >= 16 && sizeof(T) <= 8) ? 3 : 0)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
                            int nblocks, long long total_items, int noshift) {
     constexpr int TA = 32 * KA, TB = 32 * KB;

@@ -691,7 +691,18 @@ int Plan::time_backend(int backend, double* ms, bool reshapes) {
         float t = 0;
         if (!rc && ce == cudaSuccess) {
             cudaEventElapsedTime(&t, e0, e1);
-            *ms = comm_.max((double)t / std::max(1, (int)cfg_.n_measure_iters));
+            // report_timings, src/dtfft_reshape_plan_base.F90:708-731: max / min / avg over the ranks of the mean
+            // time per iteration; the max decides
+            const double mine = (double)t / std::max(1, (int)cfg_.n_measure_iters);
+            std::vector<double> all;
+            comm_.allgather_v(mine, all);
+            double mx = all[0], mn = all[0], sum = 0;
+            for (double x : all) mx = std::max(mx, x), mn = std::min(mn, x), sum += x;
+            *ms = mx;
+            log("  %s %s:", reshapes ? "reshapes," : "transpositions,", dtfft_get_backend_string((dtfft_backend_t)backend));
+            log("    max: %.6f [ms]", mx);
+            log("    min: %.6f [ms]", mn);
+            log("    avg: %.6f [ms]", sum / (double)all.size());
         } else {
             comm_.max(1e30);
         }
