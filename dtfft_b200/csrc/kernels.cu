@@ -29,48 +29,12 @@ template <> struct ElemT<4> { using type = unsigned int; };
 template <> struct ElemT<8> { using type = uint2; };
 template <> struct ElemT<16> { using type = uint4; };
 
-// Payload accesses name the global state space explicitly: block bases come out of the descriptor table
-// (local or peer-mapped HBM), which would otherwise make them generic-space LD / ST in SASS.  The bounds predicate
-// travels INTO the instruction (@p ld.global ...): a C++ `if` around inline asm cannot be if-converted and would put a
-// branch around every load of a tile, which cost the 4-byte permutes 7 % (16 loads per thread; profiles/r02k_kbench_quick.txt).
-template <typename T>
-__device__ __forceinline__ T ld_global_if(const T* p, bool pred) {
-    const unsigned pr = pred ? 1u : 0u;
-    if constexpr (sizeof(T) == 16) {
-        uint4 v;
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
-            : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "r"(pr));
-        return *reinterpret_cast<T*>(&v);
-    } else if constexpr (sizeof(T) == 8) {
-        uint2 v;
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.v2.u32 {%0, %1}, [%2];\n\t}"
-            : "=r"(v.x), "=r"(v.y) : "l"(p), "r"(pr));
-        return *reinterpret_cast<T*>(&v);
-    } else {
-        unsigned v;
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pr));
-        return *reinterpret_cast<T*>(&v);
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ void st_global_if(T* p, const T& val, bool pred) {
-    const unsigned pr = pred ? 1u : 0u;
-    if constexpr (sizeof(T) == 16) {
-        const uint4 v = *reinterpret_cast<const uint4*>(&val);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
-                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(pr)
-                     : "memory");
-    } else if constexpr (sizeof(T) == 8) {
-        const uint2 v = *reinterpret_cast<const uint2*>(&val);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(v.x),
-                     "r"(v.y), "r"(pr)
-                     : "memory");
-    } else {
-        const unsigned v = *reinterpret_cast<const unsigned*>(&val);
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pr) : "memory");
-    }
-}
+// Payload accesses are plain C++ loads / stores under their bounds test (the compiler turns them into predicated
+// LDG / STG and batches them freely); block bases come out of the descriptor table (local or peer-mapped HBM), so the
+// kernels tell the compiler that they are global-space addresses -- __builtin_assume(__isGlobal(p)) -- which keeps them
+// LDG / STG instead of generic LD / ST.  (Inline-asm ld.global / st.global was measured too: a C++ `if` around the asm put
+// a branch around every load (4-byte permutes -7 %), the predicate inside the asm cost the 8-byte permutes 15 %;
+// profiles/r02k_kbench_quick.txt, r02_kbench_quick.txt, r02l_kbench_quick.txt.)
 
 __device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
     return f.mul ? (__umulhi(n, f.mul) >> f.shr) : n;
@@ -120,10 +84,8 @@ __device__ __forceinline__ bool peer_abort(const BlockDesc* __restrict__ blocks,
 // ---------------------------------------------------------------------------------
 // Family T
 // ---------------------------------------------------------------------------------
-// 512-thread instantiations must keep three CTAs per SM (<= 42 registers): the 8-byte permutes lost 15 % when the
-// build used 50 (profiles/r02_kbench_quick.txt vs r02a_kbench_hint0.txt).
 template <typename T, int KA, int KB, int ROWS>
-__global__ void __launch_bounds__(32 * ROWS, (ROWS >= 16 && sizeof(T) <= 8) ? 3 : 0)
+__global__ void __launch_bounds__(32 * ROWS)
     transpose_tiles_kernel(const T* __restrict__ in, T* __restrict__ out, const BlockDesc* __restrict__ blocks,
                            int nblocks, long long total_items, int noshift) {
     constexpr int TA = 32 * KA, TB = 32 * KB;
@@ -149,6 +111,8 @@ __global__ void __launch_bounds__(32 * ROWS, (ROWS >= 16 && sizeof(T) <= 8) ? 3 
         const long long is1 = d.is1, os0 = d.os0;
         const T* src = (d.in_base ? reinterpret_cast<const T*>(d.in_base) : in) + d.in_off + (long long)p.c * d.is2;
         T* dst = (d.out_base ? reinterpret_cast<T*>(d.out_base) : out) + d.out_off + (long long)p.c * d.os2;
+        __builtin_assume(__isGlobal(src));
+        __builtin_assume(__isGlobal(dst));
         // Destination runs that start off a 128-byte line (uneven splits: 250 x 8 B ...) would make every tile boundary
         // split a line between two warps: partial-line stores, ruinous over NVLink (config 5, Y->Z: 204 GB/s).  The
         // table builder shifts the tile grid back by d.bshift elements instead; the first tile is masked at its start.
@@ -161,7 +125,7 @@ __global__ void __launch_bounds__(32 * ROWS, (ROWS >= 16 && sizeof(T) <= 8) ? 3 
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int a = a0 + tx + 32 * k;
-                regs[j][k] = ld_global_if(src + a + (long long)b * is1, a < n0 && b >= 0 && b < n1);
+                if (a < n0 && b >= 0 && b < n1) regs[j][k] = src[a + (long long)b * is1];
             }
         }
 #pragma unroll
@@ -175,7 +139,7 @@ __global__ void __launch_bounds__(32 * ROWS, (ROWS >= 16 && sizeof(T) <= 8) ? 3 
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int b = b0 + tx + 32 * k;
-                st_global_if(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k], a < n0 && b >= 0 && b < n1);
+                if (a < n0 && b >= 0 && b < n1) dst[(long long)a * os0 + b] = tile[(j * ROWS + ty) * PITCH + tx + 32 * k];
             }
         }
         __syncthreads();
@@ -252,6 +216,8 @@ __global__ void __launch_bounds__(kRowsThreads)
         const long long is1 = d.is1, os1 = d.os1;
         const V* src = (d.in_base ? reinterpret_cast<const V*>(d.in_base) : in) + d.in_off + (long long)p.c * d.is2;
         V* dst = (d.out_base ? reinterpret_cast<V*>(d.out_base) : out) + d.out_off + (long long)p.c * d.os2;
+        __builtin_assume(__isGlobal(src));
+        __builtin_assume(__isGlobal(dst));
         const int col = p.t0 * TX + tx;
         const int row0 = p.t1 * (TY * UR) + ty;
         if (col < n0) {
@@ -259,12 +225,12 @@ __global__ void __launch_bounds__(kRowsThreads)
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                regs[r] = ld_global_if(src + col + (long long)row * is1, row < n1);
+                if (row < n1) regs[r] = src[col + (long long)row * is1];
             }
 #pragma unroll
             for (int r = 0; r < UR; ++r) {
                 const int row = row0 + r * TY;
-                st_global_if(dst + col + (long long)row * os1, regs[r], row < n1);
+                if (row < n1) dst[col + (long long)row * os1] = regs[r];
             }
         }
     }
