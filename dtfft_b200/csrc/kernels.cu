@@ -33,8 +33,18 @@ template <> struct ElemT<16> { using type = uint4; };
 // LDG / STG and batches them freely); block bases come out of the descriptor table (local or peer-mapped HBM), so the
 // kernels tell the compiler that they are global-space addresses -- __builtin_assume(__isGlobal(p)) -- which keeps them
 // LDG / STG instead of generic LD / ST.  (Inline-asm ld.global / st.global was measured too: a C++ `if` around the asm put
-// a branch around every load (4-byte permutes -7 %), the predicate inside the asm cost the 8-byte permutes 15 %;
-// profiles/r02k_kbench_quick.txt, r02_kbench_quick.txt, r02l_kbench_quick.txt.)
+// a branch around every load (4-byte permutes -7 %), the predicate inside the asm cost the 8-byte permutes 15 % but is
+// the fastest form for 4-byte elements (6.6 vs 6.1-6.4 TB/s: 16 loads per thread); profiles/r02k_kbench_quick.txt,
+// r02_kbench_quick.txt, r02l_kbench_quick_isglobal.txt.  Hence: 4-byte tiles use the predicated-asm accessors below,
+// 8- and 16-byte tiles plain C++.)
+__device__ __forceinline__ unsigned ld_global_if(const unsigned* p, bool pred) {
+    unsigned v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.u32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"(pred ? 1u : 0u));
+    return v;
+}
+__device__ __forceinline__ void st_global_if(unsigned* p, unsigned v, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v), "r"(pred ? 1u : 0u) : "memory");
+}
 
 __device__ __forceinline__ unsigned fast_div(unsigned n, const FastDiv& f) {
     return f.mul ? (__umulhi(n, f.mul) >> f.shr) : n;
@@ -125,7 +135,11 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KA; ++k) {
                 const int a = a0 + tx + 32 * k;
-                if (a < n0 && b >= 0 && b < n1) regs[j][k] = src[a + (long long)b * is1];
+                if constexpr (sizeof(T) == 4) {
+                    regs[j][k] = ld_global_if(src + a + (long long)b * is1, a < n0 && b >= 0 && b < n1);
+                } else {
+                    if (a < n0 && b >= 0 && b < n1) regs[j][k] = src[a + (long long)b * is1];
+                }
             }
         }
 #pragma unroll
@@ -139,7 +153,11 @@ __global__ void __launch_bounds__(32 * ROWS)
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int b = b0 + tx + 32 * k;
-                if (a < n0 && b >= 0 && b < n1) dst[(long long)a * os0 + b] = tile[(j * ROWS + ty) * PITCH + tx + 32 * k];
+                if constexpr (sizeof(T) == 4) {
+                    st_global_if(dst + (long long)a * os0 + b, tile[(j * ROWS + ty) * PITCH + tx + 32 * k], a < n0 && b >= 0 && b < n1);
+                } else {
+                    if (a < n0 && b >= 0 && b < n1) dst[(long long)a * os0 + b] = tile[(j * ROWS + ty) * PITCH + tx + 32 * k];
+                }
             }
         }
         __syncthreads();
