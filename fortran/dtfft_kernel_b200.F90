@@ -32,6 +32,35 @@ public :: kernel_b200
       import
       type(c_ptr) :: kernel
     end function
+    ! One launch for every neighbour (what the non-pipelined unpack of reshape_handle_generic wants instead of the
+    ! loop of P launches, src/dtfft_kernel_device.F90:167-174).
+    integer(c_int) function dtfftb_kernel_execute_all(kernel, in, out, stream) bind(C)
+      import
+      type(c_ptr), value :: kernel, in, out, stream
+    end function
+    ! Kernel over explicit boxes (10 x n int64: n0 n1 n2 in_off out_off is1 is2 os0 os1 os2, elements) with one
+    ! destination base per box: the direct-store transposition of a fused backend (the reference's fused backends
+    ! drive pack_forward / pack_backward per peer, src/dtfft_reshape_handle_generic.F90:447).
+    integer(c_int) function dtfftb_kernel_create_boxes(kernel, family, base_storage, n_boxes, boxes, out_bases) bind(C)
+      import
+      type(c_ptr)                :: kernel
+      integer(c_int),     value  :: family         ! 2 = tiled transpose, 3 = row copy
+      integer(c_int64_t), value  :: base_storage
+      integer(c_int),     value  :: n_boxes
+      integer(c_int64_t)         :: boxes(10, *)
+      type(c_ptr),        value  :: out_bases       ! c_loc of n_boxes c_ptr (peer-mapped bases), or c_null_ptr
+    end function
+    ! Timed tile autotune with the per-candidate report of src/dtfft_kernel_device.F90:385-389 (ms and GB/s).
+    integer(c_int) function dtfftb_kernel_autotune_report(kernel, in, out, stream, n_warmup, n_iters, max_entries, &
+                                                          n_entries, tiles, ms, gbs) bind(C)
+      import
+      type(c_ptr),    value :: kernel, in, out, stream
+      integer(c_int), value :: n_warmup, n_iters, max_entries
+      integer(c_int)        :: n_entries
+      integer(c_int32_t)    :: tiles(3, *)
+      real(c_float)         :: ms(*)
+      real(c_double)        :: gbs(*)
+    end function
   end interface
 
   type, extends(abstract_kernel) :: kernel_b200

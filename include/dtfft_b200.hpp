@@ -473,6 +473,25 @@ public:
         DTFFT_CXX_CALL(detail::as_error(dtfftb_plan_get_stats(_plan, &s.kernel_launches, &s.local_bytes, &s.remote_bytes)))
         return s;
     }
+    /* NVLINK_FUSED: calls that ran on the NCCL stand-in because a buffer could not be shared through cudaIpc. */
+    int64_t get_fallbacks() const {
+        int64_t n = 0;
+        DTFFT_CXX_CALL(detail::as_error(dtfftb_plan_get_fallbacks(_plan, &n)))
+        return n;
+    }
+    /* How one transposition moves its data on this rank: 0 local kernel, 1 NCCL, 2 direct-store kernel, 3 copy engines,
+     * 4 direct-store kernel alone / copy engines in pair pipelines; copies = strided peer copies per execute. */
+    struct ExchangeForm {
+        int form = 0, copies = 0;
+    };
+    ExchangeForm get_exchange_form(Transpose transpose_type) const {
+        ExchangeForm f;
+        DTFFT_CXX_CALL(detail::as_error(dtfftb_plan_get_exchange_form(_plan, static_cast<int>(transpose_type), &f.form, &f.copies)))
+        return f;
+    }
+    /* Non-zero once a device barrier between GPUs has timed out (the plan is dead: every call returns
+     * DTFFTB_ERROR_PEER_TIMEOUT). */
+    int peer_error() const noexcept { return dtfftb_plan_peer_error(_plan); }
 
 protected:
     Plan() : _plan(nullptr) {}

@@ -61,6 +61,8 @@ def main():
     ap.add_argument("--tiles", default="1,2,8;2,2,8;2,1,8;1,4,16;1,1,8", help="ka,kb,rows;...")
     ap.add_argument("--check", action="store_true", help="verify the landed Z pencils (index-encoded)")
     ap.add_argument("--uneven", default="", help="z counts per device, e.g. 250,262: config-5-like 8-byte case (512 x z x 384)")
+    ap.add_argument("--local", action="store_true", help="--uneven on ONE device: the peers' pencils are local buffers (is the "
+                    "access pattern itself slow, or only over NVLink?)")
     args = ap.parse_args()
     if args.uneven:
         return uneven(args)
@@ -143,13 +145,37 @@ def uneven(args):
     zc = [int(v) for v in args.uneven.split(",")]
     G = len(zc)
     es, ny, nx = 8, 512, 384
+    boxes, nloc, nz_elems = uneven_case(G, zc, ny, nx)
+    if args.local:
+        torch.cuda.set_device(0)
+        dsts = [torch.zeros(nz_elems, dtype=torch.int64, device="cuda") for _ in range(G)]
+        for d in range(G):
+            srcd = torch.arange(nloc[d], dtype=torch.int64, device="cuda")
+            for tile in args.tiles.split(";"):
+                ka, kb, rows = (int(v) for v in tile.split(","))
+                k = Kernel().create_boxes(2, es, boxes[d], out_bases=dsts)
+                k.set_tile(ka, kb, rows)
+                for _ in range(args.warmup):
+                    k.execute_all(srcd, dsts[0])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.iters):
+                    k.execute_all(srcd, dsts[0])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / args.iters
+                print(json.dumps({"what": "config-5-like Y_TO_Z kernel of virtual rank %d, every destination LOCAL" % d, "z_counts": zc,
+                                  "tile": [32 * ka, 32 * kb], "ms": ms, "hbm_GBps": 2 * nloc[d] * es / (ms * 1e-3) / 1e9,
+                                  "align_tiles": os.environ.get("DTFFTB_ALIGN_TILES", "1")}), flush=True)
+                k.destroy()
+        return
     rt = ctypes.CDLL("libcudart.so.12")
     for d in range(G):
         torch.cuda.set_device(d)
         for p in range(G):
             if p != d:
                 rt.cudaDeviceEnablePeerAccess(p, 0)
-    boxes, nloc, nz_elems = uneven_case(G, zc, ny, nx)
     src, dst, streams = [], [], []
     for d in range(G):
         torch.cuda.set_device(d)
