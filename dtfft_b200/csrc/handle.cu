@@ -275,7 +275,9 @@ int ReshapeHandle::peer_bases(void* out, std::vector<void*>* bases) {
 
 int ReshapeHandle::ensure_dma_resources() {
     cudaError_t ce;
-    if (const char* e = getenv("DTFFTB_DMA_STREAMS")) n_copy_streams_ = std::max(1, std::min((int)kCopyStreams, atoi(e)));
+    // at most 4: with 7 copy streams at 8 GPUs the bench's parity block caught a mismatching first backward call
+    // (profiles/r02h_bench_n8_pairdma_streams7.json, unexplained); 1, 2 and 4 streams are parity- and stress-tested
+    if (const char* e = getenv("DTFFTB_DMA_STREAMS")) n_copy_streams_ = std::max(1, std::min(4, atoi(e)));
     for (int i = 0; i < n_copy_streams_; ++i) {
         if (!copy_streams_[i]) {
             int lo = 0, hi = 0;

@@ -188,7 +188,7 @@ private:
     std::unique_ptr<Kernel> dma_pack_;      // in -> staging, one launch per peer
     std::unique_ptr<Kernel> dma_self_;      // my own block, in -> out
     static constexpr int kCopyStreams = 8;
-    int n_copy_streams_ = 2;  // DTFFTB_DMA_STREAMS (1..8): peers are dealt round over this many copy streams
+    int n_copy_streams_ = 2;  // DTFFTB_DMA_STREAMS (1..4): peers are dealt round over this many copy streams
     cudaStream_t copy_streams_[kCopyStreams] = {};
     std::vector<cudaEvent_t> pack_done_;    // per slice
     cudaEvent_t copies_done_[kCopyStreams] = {};
