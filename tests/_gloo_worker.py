@@ -74,6 +74,51 @@ def main():
     for r in range(world):
         assert np.array_equal(dsts[r], want[r]), r
     plan.destroy()
+
+    # (3) the copy-engine form of an exchanging transposition (geometry.h: DmaBlock) across real processes: every rank's
+    #     (peer, slice) packs and strided 3-D copies, gathered and replayed against the datatype truth, whole and sliced
+    from tests.test_plan_host import _dma_copy
+
+    for sub in (None, "2048"):
+        if sub is None:
+            os.environ.pop("DTFFTB_DMA_SUB_BYTES", None)
+        else:
+            os.environ["DTFFTB_DMA_SUB_BYTES"] = sub
+        dims = [96, 40, 64]  # x = 96: Y -> Z blocks can be cut into 3 slices along the source's slowest axis
+        plan = PlanC2C(dims, comm=TorchComm(cart_dims=[1, 1, world]), config=Config(enable_z_slab=False), dry=True)
+        comm_dims = plan.grid_dims
+        G = P.global_array(dims, np.complex128, kind="index")
+        nsliced = 0
+        for t in (2, -2):
+            d = plan.describe_dma(t)
+            mine = (d["members"], d["me"], [(e["member"], e["nsub"], e["pack"].tolist(), e["fused"].tolist(), e["copy"]) for e in d["entries"]])
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            src = P.scatter_input(G, dims, comm_dims, t)
+            want = P.transpose_datatype(G, dims, comm_dims, t)
+            out = [np.full(w.size, np.complex128(-7 - 7j)) for w in want]
+            hits = [np.zeros(w.size, np.int32) for w in want]
+            for r in range(world):
+                members, me, entries = gathered[r]
+                remote = sum(int(np.prod(f[:3])) for (m, _, _, f, _) in entries if m != me and f[0] > 0)
+                staging = np.zeros(max(remote, 1), np.complex128)
+                for (m, nsub, pack, f, cp) in entries:
+                    nsliced += nsub > 1
+                    if f[0] <= 0:
+                        continue
+                    if m == me:
+                        P.apply_boxes(src[r], out, [f], [members[m]])
+                        P.apply_boxes(np.ones(src[r].size, np.int32), hits, [f], [members[m]])
+                        continue
+                    assert cp["ok"] == 1
+                    P.apply_boxes(src[r], [staging], [pack], [0])
+                    _dma_copy(staging, out[members[m]], cp, int(pack[4]))
+                    _dma_copy(np.ones(staging.size, np.int32), hits[members[m]], cp, int(pack[4]))
+            for r in range(world):
+                assert np.array_equal(out[r], want[r]) and np.all(hits[r] == 1), (t, r, sub)
+        assert (nsliced > 0) == (sub is not None), (nsliced, sub)
+        plan.destroy()
+    os.environ.pop("DTFFTB_DMA_SUB_BYTES", None)
     Config()._commit()
     dist.barrier()
     dist.destroy_process_group()
