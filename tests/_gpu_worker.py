@@ -100,7 +100,10 @@ def main():
             plan.destroy()
 
         # FFT parity: C2C fp64 and R2C fp32 (tolerances of BASELINE.json north_star)
-        for cls, dims, prec, rdt, cdt, tol in ((PlanC2C, [64, 48, 40], Precision.DOUBLE, np.complex128, np.complex128, 1e-12),
+        # ([64, 64, 64] C2C fp64 on pencils is BASELINE.json configs[0]; with 4 ranks sharing one GPU
+        #  -- tests/test_zz_shared_device_gpu.py -- it runs at the reference's own 4 ranks on the driver's box)
+        for cls, dims, prec, rdt, cdt, tol in ((PlanC2C, [64, 64, 64], Precision.DOUBLE, np.complex128, np.complex128, 1e-12),
+                                               (PlanC2C, [64, 48, 40], Precision.DOUBLE, np.complex128, np.complex128, 1e-12),
                                                (PlanR2C, [66, 40, 36], Precision.SINGLE, np.float32, np.complex64, 1e-5),
                                                (PlanC2C, [64, 96], Precision.DOUBLE, np.complex128, np.complex128, 1e-12)):
             # NVLINK_FUSED also runs with the FFT <-> exchange stage overlap (3 uneven chunks)
