@@ -25,7 +25,8 @@ extern "C" {
 #define DTFFTB_ERROR_CUDA_BASE (-10000)
 #define DTFFTB_ERROR_NCCL_BASE (-20000)
 #define DTFFTB_ERROR_INTERNAL (-30000) /* invariant violated (reference: INTERNAL_ERROR) */
-#define DTFFTB_ERROR_NOT_REGISTERED (-30001) /* NVLINK_FUSED backend: `out` is not a registered (dtfft_mem_alloc) buffer */
+#define DTFFTB_ERROR_NOT_REGISTERED (-30001) /* NVLINK_FUSED backend: `out` cannot be shared with the peers through cudaIpc and no NCCL
+                                              * communicator exists to stand in (plans always have one; plugin-level users may not) */
 #define DTFFTB_ERROR_COMM (-30002) /* the host allgather callback failed */
 #define DTFFTB_ERROR_PEER_TIMEOUT (-30003) /* NVLINK_FUSED backend: a group member did not reach a device barrier within
                                             * DTFFTB_PEER_TIMEOUT_MS (default 20000): the kernels of the group stored nothing

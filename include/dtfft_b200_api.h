@@ -331,9 +331,13 @@ dtfft_error_t dtfft_create_config(dtfft_config_t* config);
 dtfft_error_t dtfft_set_config(const dtfft_config_t* config);
 
 /* ---- extensions of this library (not in the reference) --------------------------------- */
-/* Register / unregister a user-allocated device buffer for DTFFT_BACKEND_NVLINK_FUSED.
- * Collective: every rank calls it in the same order with its own buffer of the same role.
- * Buffers from dtfft_mem_alloc are registered automatically. */
+/* DTFFT_BACKEND_NVLINK_FUSED takes ANY device pointer (like the reference, src/dtfft_plan.F90:1769-1795): the first call
+ * with a given destination publishes the allocation behind it to the peers (collective, over cudaIpc), a re-allocated
+ * address is detected and re-published, memory cudaIpc cannot share runs on an NCCL stand-in.  These two calls are
+ * therefore OPTIONAL: register_buffer maps a buffer ahead of its first use (collective: every rank calls it in the same
+ * order with its own buffer of the same role; dtfft_mem_alloc does it automatically); unregister_buffer (collective) makes
+ * the peers drop their mappings before the memory is freed -- what dtfft_mem_free does for dtfft_mem_alloc'ed memory, and
+ * what a caller should do (or let the buffer outlive the plan) for memory it frees itself. */
 dtfft_error_t dtfftb_plan_register_buffer(dtfft_plan_t plan, void* ptr, size_t bytes);
 dtfft_error_t dtfftb_plan_unregister_buffer(dtfft_plan_t plan, void* ptr);
 /* Per-execute accounting of the last dtfft_execute / dtfft_transpose / dtfft_reshape on this
