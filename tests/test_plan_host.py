@@ -643,7 +643,8 @@ def test_dma_blocks_deliver_every_transposition(dims, grid, sub_bytes):
 
 
 @pytest.mark.parametrize("dims,nranks", [((24, 20, 36), 4), ((17, 13, 29), 3), ((32, 8, 16), 8), ((12, 10, 7), 2),
-                                         ((96, 80, 72), 2)])
+                                         ((96, 80, 72), 2), ((67, 5, 9), 4), ((70, 33, 11), 5), ((33, 64, 6), 6),
+                                         ((130, 7, 40), 3)])
 def test_peer_by_peer_pair_pipelines(dims, nranks, sub_bytes):
     """Plan::run_transpose_pair with copy-engine exchanges on a slab-shaped grid 1 x 1 x P.  Forward: the local X->Y
     runs in pieces cut by the (peer, slice) blocks of the Y->Z exchange; after a piece the pack of that slice must
@@ -732,3 +733,76 @@ def test_peer_by_peer_pair_pipelines(dims, nranks, sub_bytes):
         assert np.array_equal(outX[r], wantX[r]), r  # a piece that read ahead of its slice would have copied the sentinel
         assert np.all(hitsX[r] == 1), r
     Config()._commit()
+
+
+def _random_dma_cases(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_cases):
+        nd_ = int(rng.choice([2, 3, 3]))
+        if nd_ == 2:
+            p = int(rng.choice([2, 3, 4, 5]))
+            grid = [1, p]
+            dims = [int(rng.integers(p, 60)), int(rng.integers(p, 60))]
+        else:
+            g1, g2 = int(rng.choice([1, 2, 3])), int(rng.choice([1, 2, 3, 4]))
+            if g1 * g2 == 1:
+                g2 = 2
+            grid = [1, g1, g2]
+            dims = [int(rng.integers(max(g1, 2), 40)), int(rng.integers(max(g1, g2, 2), 40)), int(rng.integers(max(g2, 2), 40))]
+        out.append((tuple(dims), grid, str(int(rng.choice([64, 512, 4096])))))
+    return out
+
+
+@pytest.mark.parametrize("dims,grid,sub", _random_dma_cases(24, 2026))
+def test_dma_blocks_fuzz(dims, grid, sub):
+    """Random extents (primes, extents barely above the grid, uneven splits) and grids: whenever every block of a
+    transposition is expressible as one strided 3-D copy (DmaBlock::ok -- the handle falls back to the direct-store
+    kernel otherwise, for the whole group alike), packs + copies must deliver exactly the datatype truth."""
+    old = os.environ.get("DTFFTB_DMA_SUB_BYTES")
+    os.environ["DTFFTB_DMA_SUB_BYTES"] = sub
+    try:
+        nranks = int(np.prod(grid))
+        cfg = Config(enable_z_slab=False)
+        plans = dry_world(nranks, lambda r, c: PlanC2C(list(dims), comm=c, config=cfg, dry=True), cart_dims=grid)
+        comm_dims = plans[0].grid_dims
+        G = P.global_array(dims, np.complex128, kind="index")
+        SENT = np.complex128(-7 - 7j)
+        replayed = 0
+        for t in ([1, -1] if len(dims) == 2 else [1, -1, 2, -2]):
+            descr = [plan.describe_dma(t) for plan in plans]
+            if len(descr[0]["members"]) == 1:
+                continue
+            if not all(e["copy"]["ok"] == 1 for d in descr for e in d["entries"]):
+                continue  # not one pitched copy per block: this transposition keeps the direct-store kernel
+            src = P.scatter_input(G, list(dims), comm_dims, t)
+            want = P.transpose_datatype(G, list(dims), comm_dims, t)
+            out = [np.full(w.size, SENT) for w in want]
+            hits = [np.zeros(w.size, np.int32) for w in want]
+            for r, d in enumerate(descr):
+                members, me = d["members"], d["me"]
+                remote = sum(int(np.prod(e["fused"][:3])) for e in d["entries"] if e["member"] != me and e["fused"][0] > 0)
+                staging = np.full(max(remote, 1), SENT)
+                for e in d["entries"]:
+                    f, peer = e["fused"], members[e["member"]]
+                    if f[0] <= 0:
+                        continue
+                    if e["member"] == me:
+                        P.apply_boxes(src[r], out, [f], [peer])
+                        P.apply_boxes(np.ones(src[r].size, np.int32), hits, [f], [peer])
+                        continue
+                    off = int(e["pack"][4])
+                    P.apply_boxes(src[r], [staging], [e["pack"]], [0])
+                    _dma_copy(staging, out[peer], e["copy"], off)
+                    _dma_copy(np.ones(staging.size, np.int32), hits[peer], e["copy"], off)
+            for r in range(nranks):
+                assert np.array_equal(out[r], want[r]), (t, r)
+                assert np.all(hits[r] == 1), (t, r)
+            replayed += 1
+        assert replayed >= 1 or nranks == 1
+    finally:
+        if old is None:
+            os.environ.pop("DTFFTB_DMA_SUB_BYTES", None)
+        else:
+            os.environ["DTFFTB_DMA_SUB_BYTES"] = old
+        Config()._commit()
