@@ -1859,6 +1859,17 @@ int Plan::report() const {
     line("  Alloc / aux bytes    :  %zu / %zu", alloc_bytes(), aux_bytes());
     line("  Stage overlap chunks :  %d", overlap_chunks_);
     line("  CUDA graph replay    :  %s", graphs_usable() ? "True" : "False");
+    {  // how every transposition moves its data on this rank (Plan::exchange_form)
+        static const char* const tnames[7] = {"Z_TO_X", "Z_TO_Y", "Y_TO_X", "", "X_TO_Y", "Y_TO_Z", "X_TO_Z"};
+        static const char* const fnames[5] = {"local kernel", "NCCL pack / send-recv / unpack", "direct-store kernel",
+                                              "copy engines", "direct-store kernel alone, copy engines in pair pipelines"};
+        for (const auto& kv : handles_) {
+            int f = 0, n = 0;
+            if (exchange_form(kv.first, &f, &n) == DTFFT_SUCCESS && kv.first >= -3 && kv.first <= 3 && kv.first != 0)
+                line("  Transpose %-6s     :  %s", tnames[kv.first + 3], fnames[f]);
+        }
+        if (stat_fallbacks_ > 0) line("  NCCL stand-in calls  :  %lld", (long long)stat_fallbacks_);
+    }
     line("**End of report**");
     fflush(stdout);
     return DTFFT_SUCCESS;
